@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of one Strang step of GEMPIC's 1d2v Hamiltonian splitting.
+
+    python bench.py --gpus N --steps K --warmup W          (ours; N>1 under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): Weibel instability 1d2v, HamiltonianSplitting{1,2},
+32 cells, degree 3/2 :galerkin, dt = 0.05, 1e8 particles per B200 (weak scaling: N GPUs hold
+N x 1e8 particles, rho/j moments all-reduced over NCCL every depositing sub-step).
+A "step" is one strang_splitting!(h, dt, 1): five streaming particle passes
+(HE, Hp2, Hp1, Hp2, HE) + the replicated field solves.
+
+value   device-resident path (fields stay on the GPU), CUDA events on the library stream.
+e2e     the reference-facing call with HOST field buffers: every step copies e1,e2,b host->device
+        and e1,e2,b,j1,j2 device->host inside the timed region (gempic_hs_strang_splitting_host),
+        exactly what the Julia shim does for the aliased e_dofs/b_dofs arrays.
+roofline  dominant kernel = operatorHp1 pass: 48 algorithmic B/particle
+        over its mean device time, measured with CUDA events inside the timed region.
+cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/, "port";
+        Julia is not installed, so the reference itself cannot run) with OpenMP chunking like
+        the reference's Threads.@spawn chunks, on a bounded particle sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ---- workload (test/test_vm_1d2v.jl:11-31) ----------------------------
+K_WEIBEL = 1.25
+L_WEIBEL = 5.02654824574          # xmax of test_vm_1d2v.jl:21 (2 pi / k)
+SIGMA = (0.2, 0.005773502691896)
+BETA = 1e-4
+NX = 32
+DT = 0.05
+DEG = 3
+BYTES = {"operatorHE": 40, "operatorHp2": 40, "operatorHp1": 48, "strang_step": 208}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def weibel_b0(mod, mx):
+    """B3(0) = beta cos(kx) through l2projection! (test_vm_1d2v.jl:33,80-84)"""
+    b = np.zeros(NX)
+    mx.l2projection(b, lambda x: BETA * math.cos(2 * math.pi * x / L_WEIBEL), DEG - 1)
+    return b
+
+
+# =============================== CPU reference arm ==============================================
+def cpu_reference(n_cpu: int, steps: int, warmup: int, threads: int | None = None):
+    """Times the oracle's strang_splitting (C restatement of src/hamiltonian_splitting_1d2v.jl,
+    OpenMP over particle chunks with private deposit buffers like the reference's @spawn chunks)."""
+    from oracle import oracle as orc
+
+    orc.build()
+    cores = threads or orc.max_threads()
+    n_cpu -= n_cpu % cores
+    rng = np.random.default_rng(1234)
+    mesh = orc.OneDGrid(0.0, L_WEIBEL, NX)
+    pg = orc.ParticleGroup(1, 2, n_cpu)
+    pg.array[0] = rng.uniform(0, L_WEIBEL, n_cpu)
+    pg.array[1] = SIGMA[0] * rng.normal(size=n_cpu)
+    pg.array[2] = SIGMA[1] * rng.normal(size=n_cpu)
+    pg.array[3] = L_WEIBEL
+    ks0 = orc.ParticleMeshCoupling1D(mesh, n_cpu, DEG, "galerkin")
+    ks1 = orc.ParticleMeshCoupling1D(mesh, n_cpu, DEG - 1, "galerkin")
+    mx = orc.Maxwell1DFEM(mesh, DEG)
+    e1, e2, rho = np.zeros(NX), np.zeros(NX), np.zeros(NX)
+    b = weibel_b0(orc, mx)
+    orc.solve_poisson(e1, pg, ks0, mx, rho)
+    h = orc.HamiltonianSplitting(1, 2, mx, ks0, ks1, pg, [e1, e2], b, n_chunks=cores)
+    for _ in range(warmup):
+        h.strang_splitting(DT, 1)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        h.strang_splitting(DT, 1)
+    dt = time.perf_counter() - t0
+    return {"value": n_cpu * steps / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{n_cpu} particles x {steps} Strang steps (same Weibel 1d2v config), C restatement of the "
+                      f"reference Julia path with OpenMP chunks -- Julia unavailable", "seconds": dt}, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n_cpu = args.cpu_particles
+    base, sec_per_step = cpu_reference(n_cpu, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "particle-steps/s per Strang step", "value": base["value"], "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, n_cpu, note="CPU arm: bounded sample of the same workload on the host cores"),
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, n_per_gpu, note=None):
+    cfg = {"workload": "Weibel instability 1d2v HamiltonianSplitting, 32 cells, deg 3/2 galerkin, dt 0.05 "
+                       "(BASELINE configs[1])",
+           "particles_per_gpu": int(n_per_gpu), "n_cells": NX, "spline_degree": [DEG, DEG - 1], "dt": DT,
+           "parallelism": f"particles sharded over {args.gpus} GPU(s), NCCL allreduce of rho/j",
+           "l2_policy": "inputs (32 B/particle x N >> 126 MB L2) stream from HBM every pass; no flush needed",
+           "kernels": "fused" if args.fuse else "one pass per reference operator"}
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+# =============================== GPU arm ==========================================================
+def run_ours(args):
+    import torch
+
+    import __graft_entry__ as ge
+
+    gp = ge.load_package()
+    dc = gp.DistributedContext()
+    if dc.world_size != args.gpus and dc.world_size > 1:
+        args.gpus = dc.world_size
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: libgempic_b200 has no CPU path")
+    dc.init_library_comm()
+    L = gp.load()
+    n_local = args.particles
+    n_global = n_local * dc.world_size
+    first = dc.rank * n_local
+
+    mesh = gp.OneDGrid(0.0, L_WEIBEL, NX)
+    pg = gp.ParticleGroup(1, 2, n_local, common_weight=1.0 / n_global)
+    pg.sample("uniform", 0.0, L_WEIBEL, sigma=SIGMA, seed=1234, first_index=first)
+    ks0 = gp.ParticleMeshCoupling1D(mesh, n_local, DEG, "galerkin")
+    ks1 = gp.ParticleMeshCoupling1D(mesh, n_local, DEG - 1, "galerkin")
+    mx = gp.Maxwell1DFEM(mesh, DEG)
+    e1, e2, rho = np.zeros(NX), np.zeros(NX), np.zeros(NX)
+    b = weibel_b0(gp, mx)
+    gp.solve_poisson(e1, pg, ks0, mx, rho)
+    total_charge = float(rho.sum())
+
+    h = gp.HamiltonianSplitting(1, 2, mx, ks0, ks1, pg, [e1, e2], b, resident=True)
+    if args.fuse:
+        h.set_fusion(True)
+
+    stream = torch.cuda.ExternalStream(gp.stream_ptr(), device=torch.device("cuda", dc.local_rank))
+
+    def timed(fn, steps):
+        dc.barrier()
+        gp.synchronize()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(steps):
+            fn()
+        ev1.record(stream)
+        gp.synchronize()
+        torch.cuda.synchronize()
+        dc.barrier()
+        return dc.max_over_ranks(ev0.elapsed_time(ev1))   # ms, max over ranks
+
+    # ---- value: device-resident -------------------------------------------------------------
+    step = lambda: h.strang_splitting(DT, 1)
+    for _ in range(args.warmup):
+        step()
+    gp.synchronize()
+    sampler = ClockSampler(dc.local_rank)
+    if dc.rank == 0:
+        sampler.start()
+    _lib = sys.modules["gempic_jl_b200._lib"]
+    _lib.check(L.gempic_profile_enable(C.c_int(1)))
+    gp.launch_count(reset=True)
+    ms = timed(step, args.steps)
+    launches = gp.launch_count()
+    prof = {}
+    slot = 0
+    while True:
+        tag = C.create_string_buffer(64)
+        t, cnt = C.c_double(), C.c_int64()
+        rc = L.gempic_profile_read(C.c_int(slot), tag, C.c_int(64), C.byref(t), C.byref(cnt))
+        if rc != 0:
+            break
+        prof[tag.value.decode()] = (t.value, cnt.value)
+        slot += 1
+    _lib.check(L.gempic_profile_enable(C.c_int(0)))
+    clocks = sampler.stop() if dc.rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = n_global * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host field buffers every step ---------------------------------------------------
+    h.sync_fields()
+    h_host = gp.HamiltonianSplitting(1, 2, mx, ks0, ks1, pg, [e1, e2], b, resident=False)
+    if args.fuse:
+        h_host.set_fusion(True)
+    for _ in range(min(args.warmup, 3)):
+        h_host.strang_splitting(DT, 1)
+    e2e_steps = args.steps
+    dc.barrier()
+    gp.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        h_host.strang_splitting(DT, 1)      # synchronous: H2D fields, 5 passes + solves, D2H fields
+    gp.synchronize()
+    e2e_s = dc.max_over_ranks(time.perf_counter() - t0)
+    e2e_value = n_global * e2e_steps / e2e_s
+
+    # ---- sanity: the timed state is a real simulation -------------------------------------------
+    rho2, ep = np.zeros(NX), np.zeros(NX)
+    gp.solve_poisson(ep, pg, ks0, mx, rho2)
+    assert abs(rho2.sum() - L_WEIBEL) < 1e-9 * L_WEIBEL and abs(total_charge - L_WEIBEL) < 1e-9 * L_WEIBEL, \
+        "charge is not conserved -- the step did not do its work"
+    assert np.all(np.isfinite(e1)) and np.all(np.isfinite(b))
+
+    if dc.rank == 0:
+        peak, peak_src = peaks()
+        dom = "operatorHp1"
+        roof = None
+        if dom in prof and prof[dom][1] > 0:
+            t_ms = prof[dom][0] / prof[dom][1]
+            achieved = BYTES[dom] * n_local / (t_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "k_pass<OpHp1<3,2,false>> (operatorHp1 pass)", "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_particle": BYTES[dom], "avg_launch_ms": t_ms,
+                    "all_passes": {k: {"avg_ms": v[0] / max(v[1], 1), "launches": v[1],
+                                       "GBps": BYTES.get(k, 0) * n_local / (v[0] / max(v[1], 1) * 1e-3) / 1e9 if v[1] else None}
+                                   for k, v in prof.items()},
+                    "step_GBps_vs_208B": BYTES["strang_step"] * n_local / (ms_per_step * 1e-3) / 1e9}
+        n_cpu = args.cpu_particles
+        cpu = None
+        if args.gpus == 1 and not args.no_cpu:
+            cpu, _ = cpu_reference(n_cpu, args.cpu_steps, 1)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {
+            "metric": "particle-steps/s per Strang step", "value": value, "unit": "particle-steps/s", "n_gpus": dc.world_size,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, n_local),
+            "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 3 * NX * 8,
+                    "d2h_bytes_per_step": 5 * NX * 8, "steps": e2e_steps,
+                    "what": "gempic_hs_strang_splitting_host: host e1,e2,b in, e1,e2,b,j1,j2 out, synchronous"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    dc.finalize()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=100_000_000, help="particles per GPU")
+    ap.add_argument("--cpu-particles", type=int, default=4_000_000, help="bounded sample for the CPU arm")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--fuse", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3   # timing rule: W >= 3
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,122 @@
+// common.cuh -- runtime context, handle registry and error plumbing of libgempic_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/gempic_b200.h"
+
+namespace gempic {
+
+// ---- errors ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+struct Fail {
+    int code;
+};  // thrown inside the library, converted to a status at the C boundary
+
+[[noreturn]] void fail(int code, const char *fmt, ...);
+
+#define GP_CUDA(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            ::gempic::fail(GEMPIC_ECUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, \
+                           cudaGetErrorString(_e));                                          \
+    } while (0)
+
+#define GP_REQUIRE(cond, code, ...)                  \
+    do {                                             \
+        if (!(cond)) ::gempic::fail(code, __VA_ARGS__); \
+    } while (0)
+
+// ---- context --------------------------------------------------------------------------
+struct Context {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    bool use_graphs = true;
+    // multi-GPU
+    void *nccl_comm = nullptr;
+    int n_ranks = 1, rank = 0;
+    double *pinned = nullptr;  // small pinned staging buffer for field I/O
+    size_t pinned_bytes = 0;
+};
+Context &ctx();
+void require_init();
+inline void count_launch(int n = 1) { ctx().launches += n; }
+// optional per-kernel device timing (CUDA events around each tagged launch, no host sync);
+// read back with gempic_profile_read after a synchronize
+void profile_begin(const char *tag);
+void profile_end(const char *tag);
+// sum-allreduce `n` doubles in place on the library stream (no-op for one rank)
+void allreduce_sum(double *dev, int64_t n);
+
+// ---- device buffers -------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count) GP_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void zero(cudaStream_t s) { if (n) GP_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+};
+
+void h2d(double *dev, const double *host, size_t n);  // synchronous w.r.t. the host buffer
+void d2h(double *host, const double *dev, size_t n);  // synchronises the library stream
+
+// ---- objects behind handles -----------------------------------------------------------
+enum class Kind : uint32_t { ParticleGroup = 1, Pmc1D, Pmc2D, Maxwell1D, Splitting, Boris, Maxwell2D };
+
+struct Object {
+    Kind kind;
+    explicit Object(Kind k) : kind(k) {}
+    virtual ~Object() = default;
+};
+
+gempic_handle register_object(std::unique_ptr<Object> obj);
+Object *lookup(gempic_handle h, Kind kind, const char *what);
+void destroy(gempic_handle h, Kind kind, const char *what);
+void destroy_all();
+
+template <typename T>
+T *get(gempic_handle h, const char *what)
+{
+    return static_cast<T *>(lookup(h, T::kKind, what));
+}
+
+}  // namespace gempic
+
+// Converts exceptions into status codes at every extern "C" entry point.
+#define GP_API_BEGIN try {
+#define GP_API_END                                              \
+    return GEMPIC_OK;                                           \
+    }                                                           \
+    catch (const ::gempic::Fail &f) { return f.code; }          \
+    catch (const std::exception &e)                             \
+    {                                                           \
+        ::gempic::set_error("internal error: %s", e.what());    \
+        return GEMPIC_ECUDA;                                    \
+    }

@@ -1,0 +1,135 @@
+// launch.cuh -- host-side launch planning for k_pass instantiations.
+#pragma once
+#include "ops1d.cuh"
+
+namespace gempic {
+
+// Scratch for per-block partial sums, grown on demand, owned by the context user.
+struct PartialScratch {
+    DevBuf<double> buf;
+    double *ensure(size_t n)
+    {
+        if (buf.n < n) buf.alloc(n);
+        return buf.p;
+    }
+};
+
+// LANE mode is used while one block's private copies stay below this many bytes, which
+// keeps >= 2 blocks (8 warps) resident per SM.
+constexpr size_t kLanePrivateMaxBytes = 100 * 1024;
+constexpr size_t kSmemBudget = 200 * 1024;
+
+struct LaunchInfo {
+    int grid = 0;
+    size_t smem = 0;
+    bool lane_private = false;
+    int copies = 0;
+};
+
+template <class Op>
+inline LaunchInfo plan_pass(const PassParams<Op> &P)
+{
+    LaunchInfo L;
+    const size_t field_bytes = (size_t)Op::NF * P.m.n * sizeof(double);
+    if (!Op::DEPOSIT) {
+        L.lane_private = true;
+        L.smem = field_bytes;
+        return L;
+    }
+    const size_t lp = (size_t)P.n_acc * 32 * kWarps * sizeof(double);
+    if (lp <= kLanePrivateMaxBytes) {
+        L.lane_private = true;
+        L.smem = field_bytes + lp;
+    } else {
+        const size_t one = (size_t)P.n_acc * sizeof(double);
+        GP_REQUIRE(field_bytes + one <= kSmemBudget, GEMPIC_EINVAL,
+                   "deposit grid of %d dofs does not fit in shared memory", P.n_acc);
+        size_t copies = (kSmemBudget / 2 - field_bytes) / one;
+        if (copies < 1) copies = 1;
+        if (copies > (size_t)kWarps) copies = kWarps;
+        L.lane_private = false;
+        L.copies = (int)copies;
+        L.smem = field_bytes + copies * one;
+    }
+    return L;
+}
+
+template <class Op, bool LP>
+inline int configure_kernel(size_t smem)
+{
+    auto kern = k_pass<Op, LP>;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int per_sm = 0;
+    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
+    return per_sm;
+}
+
+// Launch one pass. For deposit ops the reduced accumulators (n_acc doubles) land in `out`
+// (device) through `scratch`.  `out` may be null for non-deposit ops.
+template <class Op>
+inline void launch_pass(PassParams<Op> P, PartialScratch *scratch, double *out, const char *tag = nullptr)
+{
+    Context &c = ctx();
+    if (P.n_particles <= 0) {
+        if (Op::DEPOSIT && out) GP_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * P.n_acc, c.stream));
+        return;
+    }
+    LaunchInfo L = plan_pass(P);
+    const int per_sm = L.lane_private ? configure_kernel<Op, true>(L.smem) : configure_kernel<Op, false>(L.smem);
+    GP_REQUIRE(per_sm >= 1, GEMPIC_EINVAL, "pass does not fit on an SM (smem %zu B)", L.smem);
+    int grid = c.sm_count * per_sm;
+    const int64_t pairs = (P.n_particles + 1) / 2;
+    const int64_t need = (pairs + kBlock - 1) / kBlock;
+    if (need < grid) grid = (int)need;
+    P.copies = L.copies;
+    if (Op::DEPOSIT) P.partials = scratch->ensure((size_t)grid * P.n_acc);
+    if (tag) profile_begin(tag);
+    if (L.lane_private)
+        k_pass<Op, true><<<grid, kBlock, L.smem, c.stream>>>(P);
+    else
+        k_pass<Op, false><<<grid, kBlock, L.smem, c.stream>>>(P);
+    GP_CUDA(cudaGetLastError());
+    if (tag) profile_end(tag);
+    count_launch();
+    if (Op::DEPOSIT) {
+        const int warps_per_block = 4;
+        const int blocks = (P.n_acc + warps_per_block - 1) / warps_per_block;
+        k_reduce_partials<<<blocks, warps_per_block * 32, 0, c.stream>>>(P.partials, grid, P.n_acc, out);
+        GP_CUDA(cudaGetLastError());
+        count_launch();
+    }
+}
+
+// Degree dispatch: D0 in 1..3, D1 in {D0-1, D0}  (the reference's Maxwell1DFEM supports
+// degree 1..3 with s_deg_1 = degree-1; test_vm_1d2v.jl uses equal degrees)
+#define GP_DISPATCH_DEGREES(D0v, D1v, ...)                                                    \
+    do {                                                                                       \
+        const int _k = (D0v) * 10 + (D1v);                                                     \
+        switch (_k) {                                                                          \
+        case 10: { constexpr int D0 = 1, D1 = 0; __VA_ARGS__; } break;                                \
+        case 11: { constexpr int D0 = 1, D1 = 1; __VA_ARGS__; } break;                                \
+        case 21: { constexpr int D0 = 2, D1 = 1; __VA_ARGS__; } break;                                \
+        case 22: { constexpr int D0 = 2, D1 = 2; __VA_ARGS__; } break;                                \
+        case 32: { constexpr int D0 = 3, D1 = 2; __VA_ARGS__; } break;                                \
+        case 33: { constexpr int D0 = 3, D1 = 3; __VA_ARGS__; } break;                                \
+        default:                                                                               \
+            ::gempic::fail(GEMPIC_EINVAL, "unsupported spline degree pair (%d, %d)", (D0v), (D1v)); \
+        }                                                                                      \
+    } while (0)
+
+#define GP_DISPATCH_DEGREE(Dv, ...)                                                    \
+    do {                                                                               \
+        switch (Dv) {                                                                  \
+        case 0: { constexpr int D = 0; __VA_ARGS__; } break;                                  \
+        case 1: { constexpr int D = 1; __VA_ARGS__; } break;                                  \
+        case 2: { constexpr int D = 2; __VA_ARGS__; } break;                                  \
+        case 3: { constexpr int D = 3; __VA_ARGS__; } break;                                  \
+        default: ::gempic::fail(GEMPIC_EINVAL, "unsupported spline degree %d", (Dv));  \
+        }                                                                              \
+    } while (0)
+
+}  // namespace gempic

@@ -1,0 +1,157 @@
+// objects.cuh -- the device-resident objects behind the C-ABI handles.
+#pragma once
+#include "common.cuh"
+#include "launch.cuh"
+
+namespace gempic {
+
+// ParticleGroup{D,V} (src/particle_group.jl:15-46): device SoA, one fp64 row per
+// coordinate, rows ordered x1..xD, v1..vV, w1..wW like the rows of the reference array.
+struct ParticleGroup : Object {
+    static constexpr Kind kKind = Kind::ParticleGroup;
+    int D, V, W;
+    int64_t n;
+    double charge, mass, common_weight, q_over_m;
+    DevBuf<double> data;  // (D+V+W) rows of `stride` doubles
+    size_t stride = 0;    // row pitch in doubles (multiple of 32 -> 256 B aligned rows)
+    DevBuf<double> sort_tmp;
+    uint64_t generation = 0;  // bumped whenever the row pointers change (sort) -> stale graphs
+    ParticleGroup() : Object(kKind) {}
+    int rows() const { return D + V + W; }
+    double *row(int r) { return data.p + (size_t)r * stride; }
+    Rows rows1d()  // x, v1, (v2), w of a {1,1} or {1,2} group
+    {
+        Rows r;
+        r.x = row(0);
+        r.v1 = row(1);
+        r.v2 = V >= 2 ? row(2) : nullptr;
+        r.w = row(D + V);
+        return r;
+    }
+};
+
+// ParticleMeshCoupling1D (src/particle_mesh_coupling_1d.jl:26-95)
+struct Pmc1D : Object {
+    static constexpr Kind kKind = Kind::Pmc1D;
+    double xmin, xmax, Lx, delta_x, scaling;
+    int n_grid, degree, smoothing;
+    PartialScratch scratch;
+    DevBuf<double> grid_tmp;  // n_grid doubles
+    Pmc1D() : Object(kKind) {}
+    Mesh1D mesh(double Lmod) const
+    {
+        Mesh1D m;
+        m.xmin = xmin;
+        m.dx = delta_x;
+        m.Lx = Lmod;
+        m.n = n_grid;
+        m.pow2 = (n_grid & (n_grid - 1)) == 0;
+        return m;
+    }
+};
+
+// Maxwell1DFEM (src/maxwell_1d_fem.jl:29-177).  The reference diagonalises its circulant
+// operators with FFTW; here each operator is kept as the first column of the circulant
+// matrix (computed once on the host in extended precision from the same eigenvalue tables)
+// and applied on the device as a periodic convolution: no FFT, no CPU fallback.
+struct Maxwell1D : Object {
+    static constexpr Kind kKind = Kind::Maxwell1D;
+    double xmin, Lx, delta_x;
+    int n, s_deg_0, s_deg_1;
+    std::vector<double> eig_mass0, eig_mass1, eig_weak_ampere, eig_weak_poisson;  // half-complex layout
+    // device first columns: [mass0, mass1, inv_mass0, inv_mass1, weak_ampere, weak_poisson]
+    enum Col { C_MASS0 = 0, C_MASS1, C_INV_MASS0, C_INV_MASS1, C_AMPERE, C_POISSON, C_COUNT };
+    DevBuf<double> cols;  // C_COUNT * n
+    DevBuf<double> tmp;   // 4 * n scratch (host-buffer entry points)
+    Maxwell1D() : Object(kKind) {}
+    const double *col(int c) const { return cols.p + (size_t)c * n; }
+};
+
+std::unique_ptr<Maxwell1D> make_maxwell1d(double xmin, double xmax, int n_dofs, int degree);
+
+// ---- field kernels (fields1d.cu, compiled without FMA contraction) ---------------------
+void field_e_from_rho(const Maxwell1D &m, double *e, const double *rho);
+// j *= prescale (when prescale != 1), then e -= circ(inv_mass, j) / dx   (component 1: mass1, 2: mass0)
+void field_e_from_j(const Maxwell1D &m, double *e, double *j, int component, double prescale);
+void field_e_from_b(const Maxwell1D &m, double *e, double dt, const double *b);
+void field_b_from_e(const Maxwell1D &m, double *b, double dt, const double *e);
+// out[0] = sum_i c1[i] * circ(mass_deg, c2)[i] * dx
+void field_inner_product(const Maxwell1D &m, const double *c1, const double *c2, int degree, double *out);
+void field_axpby(double *y, double a, const double *x, double b, int n);   // y = a*x + b*y
+void field_copy(double *dst, const double *src, int n);
+void field_max_abs_diff(const double *a, const double *b, int n, double *out);
+
+// HamiltonianSplitting{1,2}/{1,1} (src/hamiltonian_splitting.jl:20-86)
+struct Splitting : Object {
+    static constexpr Kind kKind = Kind::Splitting;
+    int D, V;
+    Maxwell1D *maxwell;
+    Pmc1D *ks0, *ks1;
+    ParticleGroup *pg;
+    int n;
+    DevBuf<double> fields;  // e1, e2, b, j1, j2, acc(2n)   (7 * n)
+    PartialScratch scratch;
+    int fuse = 0;
+    // CUDA graph of one Strang step, keyed by dt
+    cudaGraphExec_t graph = nullptr;
+    double graph_dt = 0.0;
+    int graph_fuse = -1;
+    uint64_t graph_generation = 0;
+    Splitting() : Object(kKind) {}
+    ~Splitting() override
+    {
+        if (graph) cudaGraphExecDestroy(graph);
+    }
+    double *e1() { return fields.p; }
+    double *e2() { return fields.p + n; }
+    double *b() { return fields.p + 2 * (size_t)n; }
+    double *j1() { return fields.p + 3 * (size_t)n; }
+    double *j2() { return fields.p + 4 * (size_t)n; }
+    double *acc() { return fields.p + 5 * (size_t)n; }
+    Mesh1D mesh() const { return ks0->mesh(maxwell->Lx); }
+};
+
+// HamiltonianSplittingBoris (src/hamiltonian_splitting_boris.jl:23-88)
+struct Boris : Object {
+    static constexpr Kind kKind = Kind::Boris;
+    Maxwell1D *maxwell;
+    Pmc1D *ks0, *ks1;
+    ParticleGroup *pg;
+    int n;
+    DevBuf<double> fields;  // e1, e2, b, j1, j2, e1_mid, e2_mid, b_mid, acc(2n)  (10 * n)
+    PartialScratch scratch;
+    Boris() : Object(kKind) {}
+    double *f(int which) { return fields.p + (size_t)which * n; }  // GEMPIC_F_* order
+    double *acc() { return fields.p + 8 * (size_t)n; }
+    Mesh1D mesh() const { return ks0->mesh(maxwell->Lx); }
+};
+
+// operator implementations (hs1d.cu / boris.cu)
+void hs_operator(Splitting &h, int op, double dt, bool inside_strang);
+void hs_strang(Splitting &h, double dt, int64_t steps);
+void boris_push_v_epart(Boris &s, double dt);
+void boris_push_v_bpart(Boris &s, double dt);
+void boris_push_x_accumulate_j(Boris &s, double dt);
+void boris_staggering(Boris &s, double dt);
+void boris_strang(Boris &s, double dt, int64_t steps);
+
+// batched coupling entry points on device arrays (pmc1d.cu)
+void pmc1d_add_charge_dev(Pmc1D &p, const double *x, const double *w, int64_t n, double charge, double cw,
+                          double *rho_out /* n_grid, overwritten */);
+void pmc1d_evaluate_dev(Pmc1D &p, const double *x, int64_t n, const double *field, double *out);
+void pmc1d_add_current_dev(Pmc1D &p, const double *x_old, const double *x_new, const double *w, double qm,
+                           const double *bfield /* may be null: 1d1v variant */, double *v, int64_t n,
+                           double *j_out /* n_grid, overwritten */);
+
+// diagnostics (diag.cu): particle sums [KE, P1, P2, transfer, vvb] into out5 (device)
+void diag_particle_sums(ParticleGroup &pg, Pmc1D &ks0, Pmc1D &ks1, const Maxwell1D &m, const double *e1,
+                        const double *e2, const double *b, PartialScratch &scratch, double *out5);
+
+// particle storage helpers (particles.cu)
+void pg_upload(ParticleGroup &pg, const double *aos);
+void pg_download(ParticleGroup &pg, double *aos);
+void pg_sort_1d(ParticleGroup &pg, const Pmc1D &p);
+void pg_sample(ParticleGroup &pg, int kind, double xmin, double L, double alpha, double k, const double *sigma,
+               uint64_t seed, int64_t first_index);
+
+}  // namespace gempic

@@ -1,0 +1,177 @@
+// pass.cuh -- the one streaming skeleton every particle kernel is built from.
+//
+// A "pass" streams the SoA particle rows once (128-bit coalesced loads/stores, two
+// particles per thread per load, two independent load batches in flight), applies an Op
+// per particle, and -- if the Op deposits -- accumulates grid moments in block-private
+// shared memory, reduces them hierarchically and writes one partial vector per block.
+// A tiny second kernel (reduce_partials) sums the per-block partials in a fixed order, so
+// the deposit is run-to-run deterministic in LANE mode.
+//
+// Deposit accumulators (SURVEY section 7 "hard parts": fp64 shared atomics are CAS loops):
+//   LANE mode  every lane of every warp owns a private copy of the (tiny) periodic grid:
+//              slot(g) = warp_base[g*32 + lane]. Plain LDS/DADD/STS, no atomics, and bank
+//              conflict free for any cell pattern (a half-warp's 16 lanes x 8 B always
+//              cover the 32 banks once).  Used when 32*8*n_dofs bytes per warp fit.
+//   ATOM mode  `copies` block-shared copies, warp w adds into copy w % copies with
+//              atomicAdd(double) on shared memory. Fallback for larger grids.
+#pragma once
+#include "common.cuh"
+#include "splines.cuh"
+
+namespace gempic {
+
+constexpr int kBlock = 128;  // threads per block (4 warps)
+constexpr int kWarps = kBlock / 32;
+
+enum RowBits : int { ROW_X = 1, ROW_V1 = 2, ROW_V2 = 4, ROW_W = 8 };
+
+struct Rows {
+    double *__restrict__ x;
+    double *__restrict__ v1;
+    double *__restrict__ v2;
+    double *__restrict__ w;
+};
+
+struct Particle {
+    double x, v1, v2, w;
+};
+
+template <bool LP>
+struct Acc {
+    double *p;  // LP: warp base + lane ; ATOM: base of this warp's copy
+    __device__ __forceinline__ void add(int g, double v) const
+    {
+        if (LP) p[g * 32] += v;
+        else atomicAdd(p + g, v);
+    }
+};
+
+template <class Op>
+struct PassParams {
+    Rows r;
+    int64_t n_particles;
+    Mesh1D m;
+    const double *fields[4];  // Op::NF device field vectors of m.n doubles staged in smem
+    double *partials;         // [gridDim.x][n_acc] (deposit ops only)
+    int n_acc;                // number of accumulator dofs (Op::NG * m.n, or a scalar count)
+    int copies;               // ATOM mode: accumulator copies per block
+    typename Op::Params op;
+};
+
+template <class Op>
+__device__ __forceinline__ void load_pair(const Rows &r, int64_t pair, Particle &a, Particle &b)
+{
+    if (Op::READ & ROW_X) { double2 t = reinterpret_cast<const double2 *>(r.x)[pair]; a.x = t.x; b.x = t.y; }
+    if (Op::READ & ROW_V1) { double2 t = reinterpret_cast<const double2 *>(r.v1)[pair]; a.v1 = t.x; b.v1 = t.y; }
+    if (Op::READ & ROW_V2) { double2 t = reinterpret_cast<const double2 *>(r.v2)[pair]; a.v2 = t.x; b.v2 = t.y; }
+    if (Op::READ & ROW_W) { double2 t = reinterpret_cast<const double2 *>(r.w)[pair]; a.w = t.x; b.w = t.y; }
+}
+template <class Op>
+__device__ __forceinline__ void store_pair(const Rows &r, int64_t pair, const Particle &a, const Particle &b)
+{
+    if (Op::WRITE & ROW_X) reinterpret_cast<double2 *>(r.x)[pair] = make_double2(a.x, b.x);
+    if (Op::WRITE & ROW_V1) reinterpret_cast<double2 *>(r.v1)[pair] = make_double2(a.v1, b.v1);
+    if (Op::WRITE & ROW_V2) reinterpret_cast<double2 *>(r.v2)[pair] = make_double2(a.v2, b.v2);
+}
+template <class Op>
+__device__ __forceinline__ void load_one(const Rows &r, int64_t i, Particle &a)
+{
+    if (Op::READ & ROW_X) a.x = r.x[i];
+    if (Op::READ & ROW_V1) a.v1 = r.v1[i];
+    if (Op::READ & ROW_V2) a.v2 = r.v2[i];
+    if (Op::READ & ROW_W) a.w = r.w[i];
+}
+template <class Op>
+__device__ __forceinline__ void store_one(const Rows &r, int64_t i, const Particle &a)
+{
+    if (Op::WRITE & ROW_X) r.x[i] = a.x;
+    if (Op::WRITE & ROW_V1) r.v1[i] = a.v1;
+    if (Op::WRITE & ROW_V2) r.v2[i] = a.v2;
+}
+
+template <class Op, bool LP>
+__global__ void __launch_bounds__(kBlock) k_pass(const __grid_constant__ PassParams<Op> P)
+{
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x;
+    const int n = P.m.n;
+    // ---- stage the field dofs this op gathers from --------------------------------------
+    double *sfield = smem;
+#pragma unroll
+    for (int f = 0; f < Op::NF; ++f)
+        for (int i = tid; i < n; i += kBlock) sfield[f * n + i] = P.fields[f][i];
+    // ---- zero the block-private accumulators --------------------------------------------
+    double *sacc = smem + Op::NF * n;
+    const int n_acc = P.n_acc;
+    const int acc_words = Op::DEPOSIT ? (LP ? n_acc * 32 * kWarps : n_acc * P.copies) : 0;
+    for (int i = tid; i < acc_words; i += kBlock) sacc[i] = 0.0;
+    __syncthreads();
+
+    Acc<LP> acc;
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        acc.p = LP ? sacc + (size_t)warp * n_acc * 32 + lane : sacc + (size_t)(warp % (P.copies > 0 ? P.copies : 1)) * n_acc;
+    }
+
+    // ---- stream the particles: pairs, two batches in flight -----------------------------
+    const int64_t n_pairs = P.n_particles >> 1;
+    const int64_t T = (int64_t)gridDim.x * kBlock;
+    int64_t p = (int64_t)blockIdx.x * kBlock + tid;
+    for (; p + T < n_pairs; p += 2 * T) {
+        Particle a0, a1, b0, b1;
+        load_pair<Op>(P.r, p, a0, a1);
+        load_pair<Op>(P.r, p + T, b0, b1);
+        Op::apply(a0, P, sfield, acc);
+        Op::apply(a1, P, sfield, acc);
+        store_pair<Op>(P.r, p, a0, a1);
+        Op::apply(b0, P, sfield, acc);
+        Op::apply(b1, P, sfield, acc);
+        store_pair<Op>(P.r, p + T, b0, b1);
+    }
+    for (; p < n_pairs; p += T) {
+        Particle a0, a1;
+        load_pair<Op>(P.r, p, a0, a1);
+        Op::apply(a0, P, sfield, acc);
+        Op::apply(a1, P, sfield, acc);
+        store_pair<Op>(P.r, p, a0, a1);
+    }
+    if ((P.n_particles & 1) && blockIdx.x == 0 && tid == 0) {
+        Particle a;
+        load_one<Op>(P.r, P.n_particles - 1, a);
+        Op::apply(a, P, sfield, acc);
+        store_one<Op>(P.r, P.n_particles - 1, a);
+    }
+
+    // ---- hierarchical reduce: lanes -> warps -> one partial vector per block ------------
+    if (Op::DEPOSIT) {
+        __syncthreads();
+        double *out = P.partials + (size_t)blockIdx.x * n_acc;
+        for (int g = tid; g < n_acc; g += kBlock) {
+            double s = 0.0;
+            if (LP) {
+                for (int w = 0; w < kWarps; ++w) {
+                    const double *base = sacc + (size_t)w * n_acc * 32 + (size_t)g * 32;
+#pragma unroll 8
+                    for (int l = 0; l < 32; ++l) s += base[(l + g) & 31];  // rotated: conflict free
+                }
+            } else {
+                for (int c = 0; c < P.copies; ++c) s += sacc[(size_t)c * n_acc + g];
+            }
+            out[g] = s;
+        }
+    }
+}
+
+// out[g] = sum_b partials[b][g], b ascending; one warp per dof, fixed tree -> deterministic.
+__global__ void k_reduce_partials(const double *__restrict__ partials, int n_blocks, int n_acc,
+                                  double *__restrict__ out);
+
+// host-side launch plan of a pass
+struct PassPlan {
+    bool lane_private;
+    int copies;
+    int grid;
+    size_t smem_bytes;
+};
+
+}  // namespace gempic

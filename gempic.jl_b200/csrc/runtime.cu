@@ -1,0 +1,423 @@
+// runtime.cu -- context, handle registry, error strings, host<->device field staging and
+// the NCCL all-reduce used for the grid moments (loaded lazily with dlopen so that the
+// single-GPU path has no NCCL dependency and a host process that already carries a
+// libnccl.so.2 -- e.g. torch's -- shares it).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace gempic {
+
+static thread_local std::string g_error;
+
+void set_error(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+void fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    throw Fail{code};
+}
+
+static Context g_ctx;
+Context &ctx() { return g_ctx; }
+
+void require_init()
+{
+    GP_REQUIRE(g_ctx.ready, GEMPIC_ENOTINIT, "gempic_init() has not been called (or no CUDA device)");
+}
+
+// ---- registry -------------------------------------------------------------------------
+static std::mutex g_mu;
+static std::unordered_map<gempic_handle, std::unique_ptr<Object>> g_objects;
+static gempic_handle g_next = 0x1000;
+
+gempic_handle register_object(std::unique_ptr<Object> obj)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    gempic_handle h = g_next++;
+    g_objects[h] = std::move(obj);
+    return h;
+}
+
+Object *lookup(gempic_handle h, Kind kind, const char *what)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_objects.find(h);
+    if (it == g_objects.end() || it->second->kind != kind)
+        fail(GEMPIC_EHANDLE, "invalid %s handle 0x%llx", what, (unsigned long long)h);
+    return it->second.get();
+}
+
+void destroy(gempic_handle h, Kind kind, const char *what)
+{
+    std::unique_ptr<Object> victim;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_objects.find(h);
+        if (it == g_objects.end() || it->second->kind != kind)
+            fail(GEMPIC_EHANDLE, "invalid %s handle 0x%llx", what, (unsigned long long)h);
+        victim = std::move(it->second);
+        g_objects.erase(it);
+    }
+    if (g_ctx.ready) cudaStreamSynchronize(g_ctx.stream);
+}
+
+void destroy_all()
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_objects.clear();
+}
+
+// ---- staging ---------------------------------------------------------------------------
+// Small host vectors (field dofs) go through a pinned bump buffer so that H2D copies are
+// truly asynchronous and the caller's buffer can be reused as soon as the call returns.
+static const size_t kPinnedBytes = 1 << 20;
+static size_t g_pinned_off = 0;
+
+static void ensure_pinned()
+{
+    Context &c = ctx();
+    if (!c.pinned) {
+        GP_CUDA(cudaMallocHost(&c.pinned, kPinnedBytes));
+        c.pinned_bytes = kPinnedBytes;
+        g_pinned_off = 0;
+    }
+}
+
+void h2d(double *dev, const double *host, size_t n)
+{
+    Context &c = ctx();
+    const size_t bytes = n * sizeof(double);
+    if (bytes <= kPinnedBytes / 4) {
+        ensure_pinned();
+        if (g_pinned_off + bytes > kPinnedBytes) {
+            GP_CUDA(cudaStreamSynchronize(c.stream));
+            g_pinned_off = 0;
+        }
+        char *p = reinterpret_cast<char *>(c.pinned) + g_pinned_off;
+        std::memcpy(p, host, bytes);
+        GP_CUDA(cudaMemcpyAsync(dev, p, bytes, cudaMemcpyHostToDevice, c.stream));
+        g_pinned_off += (bytes + 255) & ~(size_t)255;
+    } else {
+        GP_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c.stream));
+        GP_CUDA(cudaStreamSynchronize(c.stream));
+        g_pinned_off = 0;
+    }
+}
+
+void d2h(double *host, const double *dev, size_t n)
+{
+    Context &c = ctx();
+    GP_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    GP_CUDA(cudaStreamSynchronize(c.stream));
+    g_pinned_off = 0;
+}
+
+// ---- per-kernel profiling ---------------------------------------------------------------
+struct ProfSlot {
+    std::string tag;
+    double ms = 0.0;
+    int64_t launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+static bool g_profile = false;
+static std::vector<ProfSlot> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t take_event()
+{
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    GP_CUDA(cudaEventCreate(&e));
+    return e;
+}
+static ProfSlot &prof_slot(const char *tag)
+{
+    for (auto &s : g_prof)
+        if (s.tag == tag) return s;
+    g_prof.emplace_back();
+    g_prof.back().tag = tag;
+    return g_prof.back();
+}
+void profile_begin(const char *tag)
+{
+    if (!g_profile) return;
+    ProfSlot &s = prof_slot(tag);
+    cudaEvent_t a = take_event(), b = take_event();
+    GP_CUDA(cudaEventRecord(a, ctx().stream));
+    s.pending.emplace_back(a, b);
+}
+void profile_end(const char *tag)
+{
+    if (!g_profile) return;
+    ProfSlot &s = prof_slot(tag);
+    GP_CUDA(cudaEventRecord(s.pending.back().second, ctx().stream));
+}
+static void profile_collect()
+{
+    for (auto &s : g_prof) {
+        for (auto &pr : s.pending) {
+            float ms = 0.f;
+            GP_CUDA(cudaEventSynchronize(pr.second));
+            GP_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+            s.ms += ms;
+            s.launches++;
+            g_event_pool.push_back(pr.first);
+            g_event_pool.push_back(pr.second);
+        }
+        s.pending.clear();
+    }
+}
+
+// ---- NCCL (dlopen) ---------------------------------------------------------------------
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static NcclApi &nccl()
+{
+    if (g_nccl.lib) return g_nccl;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    GP_REQUIRE(g_nccl.lib, GEMPIC_ENCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define GP_SYM(field, name)                                                           \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(g_nccl.lib, name)); \
+    GP_REQUIRE(g_nccl.field, GEMPIC_ENCCL, "libnccl lacks %s", name)
+    GP_SYM(GetUniqueId, "ncclGetUniqueId");
+    GP_SYM(CommInitRank, "ncclCommInitRank");
+    GP_SYM(CommDestroy, "ncclCommDestroy");
+    GP_SYM(AllReduce, "ncclAllReduce");
+    GP_SYM(GetErrorString, "ncclGetErrorString");
+#undef GP_SYM
+    return g_nccl;
+}
+
+#define GP_NCCL(expr)                                                                       \
+    do {                                                                                    \
+        ncclResult_t _r = (expr);                                                           \
+        if (_r != ncclSuccess)                                                              \
+            ::gempic::fail(GEMPIC_ENCCL, "%s failed: %s", #expr, nccl().GetErrorString(_r)); \
+    } while (0)
+
+void allreduce_sum(double *dev, int64_t n)
+{
+    Context &c = ctx();
+    if (c.n_ranks <= 1 || n <= 0) return;
+    GP_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)c.nccl_comm, c.stream));
+    count_launch();
+}
+
+}  // namespace gempic
+
+using namespace gempic;
+
+extern "C" {
+
+const char *gempic_last_error(void) { return g_error.c_str(); }
+int gempic_version(void) { return 100; }
+
+int gempic_init(int device)
+{
+    GP_API_BEGIN
+    Context &c = ctx();
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        fail(GEMPIC_ENOTINIT, "no CUDA device available (%s); libgempic_b200 has no CPU path",
+             e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    GP_REQUIRE(device >= 0 && device < count, GEMPIC_EINVAL, "device %d out of range [0,%d)", device, count);
+    if (c.ready && c.device == device) return GEMPIC_OK;
+    GP_REQUIRE(!c.ready, GEMPIC_EINVAL, "already initialised on device %d", c.device);
+    GP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GP_CUDA(cudaGetDeviceProperties(&prop, device));
+    GP_REQUIRE(prop.major == 10, GEMPIC_ENOTINIT,
+               "device %d is sm_%d%d; this library ships sm_100a code only (B200)", device, prop.major, prop.minor);
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    c.smem_optin = prop.sharedMemPerBlockOptin;
+    GP_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.ready = true;
+    GP_API_END
+}
+
+int gempic_finalize(void)
+{
+    GP_API_BEGIN
+    Context &c = ctx();
+    if (!c.ready) return GEMPIC_OK;
+    cudaStreamSynchronize(c.stream);
+    destroy_all();
+    if (c.nccl_comm) {
+        nccl().CommDestroy((ncclComm_t)c.nccl_comm);
+        c.nccl_comm = nullptr;
+        c.n_ranks = 1;
+        c.rank = 0;
+    }
+    if (c.pinned) cudaFreeHost(c.pinned);
+    c.pinned = nullptr;
+    c.pinned_bytes = 0;
+    cudaStreamDestroy(c.stream);
+    c.stream = nullptr;
+    c.ready = false;
+    GP_API_END
+}
+
+int gempic_synchronize(void)
+{
+    GP_API_BEGIN
+    require_init();
+    GP_CUDA(cudaStreamSynchronize(ctx().stream));
+    GP_API_END
+}
+
+void *gempic_stream(void) { return (void *)ctx().stream; }
+
+int gempic_device_info(int *sm_count, int64_t *free_bytes, int64_t *total_bytes)
+{
+    GP_API_BEGIN
+    require_init();
+    size_t f = 0, t = 0;
+    GP_CUDA(cudaMemGetInfo(&f, &t));
+    if (sm_count) *sm_count = ctx().sm_count;
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    GP_API_END
+}
+
+int64_t gempic_launch_count(int reset)
+{
+    int64_t v = ctx().launches;
+    if (reset) ctx().launches = 0;
+    return v;
+}
+
+int gempic_set_option(const char *name, int64_t value)
+{
+    GP_API_BEGIN
+    GP_REQUIRE(name, GEMPIC_EINVAL, "null option name");
+    if (!strcmp(name, "graphs")) ctx().use_graphs = value != 0;
+    else fail(GEMPIC_EINVAL, "unknown option '%s'", name);
+    GP_API_END
+}
+
+int gempic_profile_enable(int on)
+{
+    GP_API_BEGIN
+    require_init();
+    profile_collect();
+    g_profile = on != 0;
+    if (on) g_prof.clear();
+    GP_API_END
+}
+
+int gempic_profile_read(int slot, char *tag, int tag_len, double *ms, int64_t *launches)
+{
+    GP_API_BEGIN
+    require_init();
+    profile_collect();
+    GP_REQUIRE(slot >= 0, GEMPIC_EINVAL, "negative slot");
+    if (slot >= (int)g_prof.size()) return 100;  // end of list
+    const ProfSlot &s = g_prof[slot];
+    if (tag && tag_len > 0) {
+        std::strncpy(tag, s.tag.c_str(), tag_len - 1);
+        tag[tag_len - 1] = 0;
+    }
+    if (ms) *ms = s.ms;
+    if (launches) *launches = s.launches;
+    GP_API_END
+}
+
+int gempic_comm_unique_id(void *id128)
+{
+    GP_API_BEGIN
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    GP_REQUIRE(id128, GEMPIC_EINVAL, "null id buffer");
+    ncclUniqueId id;
+    GP_NCCL(nccl().GetUniqueId(&id));
+    std::memcpy(id128, &id, sizeof(id));
+    GP_API_END
+}
+
+int gempic_comm_init(int n_ranks, int rank, const void *id128)
+{
+    GP_API_BEGIN
+    require_init();
+    Context &c = ctx();
+    GP_REQUIRE(n_ranks >= 1 && rank >= 0 && rank < n_ranks, GEMPIC_EINVAL, "bad rank %d of %d", rank, n_ranks);
+    GP_REQUIRE(!c.nccl_comm, GEMPIC_EINVAL, "communicator already initialised");
+    if (n_ranks == 1) {
+        c.n_ranks = 1;
+        c.rank = 0;
+        return GEMPIC_OK;
+    }
+    GP_REQUIRE(id128, GEMPIC_EINVAL, "null id buffer");
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    ncclComm_t comm;
+    GP_NCCL(nccl().CommInitRank(&comm, n_ranks, id, rank));
+    c.nccl_comm = comm;
+    c.n_ranks = n_ranks;
+    c.rank = rank;
+    GP_API_END
+}
+
+int gempic_comm_finalize(void)
+{
+    GP_API_BEGIN
+    Context &c = ctx();
+    if (c.nccl_comm) {
+        cudaStreamSynchronize(c.stream);
+        GP_NCCL(nccl().CommDestroy((ncclComm_t)c.nccl_comm));
+        c.nccl_comm = nullptr;
+    }
+    c.n_ranks = 1;
+    c.rank = 0;
+    GP_API_END
+}
+
+int gempic_comm_size(void) { return ctx().n_ranks; }
+
+int gempic_comm_allreduce(double *host_inout, int64_t n)
+{
+    GP_API_BEGIN
+    require_init();
+    GP_REQUIRE(host_inout && n > 0, GEMPIC_EINVAL, "bad buffer");
+    DevBuf<double> d((size_t)n);
+    h2d(d.p, host_inout, (size_t)n);
+    allreduce_sum(d.p, n);
+    d2h(host_inout, d.p, (size_t)n);
+    GP_API_END
+}
+
+}  // extern "C"

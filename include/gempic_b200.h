@@ -1,0 +1,206 @@
+/*
+ * gempic_b200.h -- C ABI of libgempic_b200.so, the B200 (sm_100a) implementation of
+ * GEMPIC.jl's particle-mesh hot path.
+ *
+ * GEMPIC.jl has no FFI layer of its own (it is pure Julia), so the boundary sits where a
+ * Julia `ccall` shim replaces the reference's per-particle loops: one call per reference
+ * *struct-level* operation.  Each entry point names the reference interface it replaces
+ * (paths relative to the GEMPIC.jl tree).  INTEGRATION.md shows the Julia binding.
+ *
+ * Conventions
+ *   - all floating point data is fp64; sizes are int64_t; handles are opaque uint64_t.
+ *   - every function returns a gempic_status; on failure gempic_last_error() holds a
+ *     thread-local message.  GEMPIC_EINVAL mirrors the reference's ArgumentError throws,
+ *     GEMPIC_EASSERT its @assert failures.
+ *   - host pointers are borrowed for the duration of the call only.
+ *   - particle arrays cross the boundary in the reference layout: column-major
+ *     (D+V+n_weights) x N  (src/particle_group.jl:29), i.e. one record per particle.
+ *   - one device per process (gempic_init); calls on one handle are not re-entrant.
+ */
+#ifndef GEMPIC_B200_H
+#define GEMPIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint64_t gempic_handle;
+
+typedef enum {
+    GEMPIC_OK = 0,
+    GEMPIC_EINVAL = 1,   /* ArgumentError in the reference */
+    GEMPIC_EASSERT = 2,  /* @assert failure in the reference */
+    GEMPIC_EHANDLE = 3,  /* unknown / wrong-type handle */
+    GEMPIC_ECUDA = 4,    /* CUDA runtime error (message has the CUDA string) */
+    GEMPIC_ENCCL = 5,    /* NCCL error */
+    GEMPIC_ENOTINIT = 6  /* gempic_init not called / no CUDA device */
+} gempic_status;
+
+/* smoothing_type symbols of ParticleMeshCoupling1D/2D (src/particle_mesh_coupling_1d.jl:56-65) */
+enum { GEMPIC_COLLOCATION = 0, GEMPIC_GALERKIN = 1 };
+/* operators of src/hamiltonian_splitting_1d2v.jl / _1d1v.jl */
+enum { GEMPIC_OP_HP1 = 1, GEMPIC_OP_HP2 = 2, GEMPIC_OP_HE = 3, GEMPIC_OP_HB = 4 };
+/* field selectors for gempic_hs_get_field / gempic_boris_get_field */
+enum {
+    GEMPIC_F_E1 = 0, GEMPIC_F_E2 = 1, GEMPIC_F_B = 2, GEMPIC_F_J1 = 3, GEMPIC_F_J2 = 4,
+    GEMPIC_F_E1_MID = 5, GEMPIC_F_E2_MID = 6, GEMPIC_F_B_MID = 7
+};
+
+/* ---- runtime ------------------------------------------------------------------------ */
+const char *gempic_last_error(void);
+int gempic_version(void);
+/* Bind the process to CUDA device `device` and create the library stream. */
+int gempic_init(int device);
+int gempic_finalize(void);
+int gempic_synchronize(void);
+/* cudaStream_t the library launches on (for CUDA-event timing by the caller). */
+void *gempic_stream(void);
+int gempic_device_info(int *sm_count, int64_t *free_bytes, int64_t *total_bytes);
+/* Number of kernels this library has launched since the last reset (for bench.py). */
+int64_t gempic_launch_count(int reset);
+/* Per-kernel device timing: CUDA events are recorded around every particle pass while enabled
+ * (no host synchronisation). gempic_profile_read walks the slots (tag = reference operator
+ * name, accumulated milliseconds, launches); it returns 100 past the last slot. */
+int gempic_profile_enable(int on);
+int gempic_profile_read(int slot, char *tag, int tag_len, double *ms, int64_t *launches);
+/* 1: capture strang steps into CUDA graphs (default), 0: plain stream launches. */
+int gempic_set_option(const char *name, int64_t value);
+
+/* ---- multi-GPU: particles sharded by rank, grid moments all-reduced ------------------
+ * replaces reduce(+, fetch.(tasks)) (src/hamiltonian_splitting_1d2v.jl:88,108,169).
+ * One process per GPU; rank 0 creates the id, the host side broadcasts it
+ * (torch.distributed / MPI / any), every rank calls gempic_comm_init. */
+int gempic_comm_unique_id(void *id128);
+int gempic_comm_init(int n_ranks, int rank, const void *id128);
+int gempic_comm_finalize(void);
+int gempic_comm_size(void);
+/* test hook: all-reduce (sum) a host vector through the same path the operators use */
+int gempic_comm_allreduce(double *host_inout, int64_t n);
+
+/* ---- ParticleGroup{D,V} (src/particle_group.jl:15-46) -------------------------------- */
+/* common_weight == 0.0 selects the reference default 1/n_particles (:30-32).
+ * n_particles is the number of particles held by THIS rank. For a sharded run pass the
+ * global common weight explicitly (1/N_global). */
+int gempic_pg_create(int D, int V, int n_weights, int64_t n_particles, double charge, double mass,
+                     double common_weight, gempic_handle *out);
+int gempic_pg_destroy(gempic_handle pg);
+/* host AoS (D+V+W) x N  <->  device SoA */
+int gempic_pg_upload(gempic_handle pg, const double *aos);
+int gempic_pg_download(gempic_handle pg, double *aos);
+/* one SoA row (0..D+V+W-1) from/to a DEVICE pointer (e.g. a torch CUDA tensor) */
+int gempic_pg_set_row_device(gempic_handle pg, int row, const double *dev_src);
+int gempic_pg_get_row_device(gempic_handle pg, int row, double *dev_dst);
+int gempic_pg_row_ptr(gempic_handle pg, int row, double **dev_ptr);
+int gempic_pg_info(gempic_handle pg, int *D, int *V, int *n_weights, int64_t *n_particles,
+                   double *charge, double *mass, double *common_weight);
+/* Periodic counting sort of the SoA rows by cell of x1 (and x2 for D=2) on the mesh of `pmc`.
+ * Stable. If `perm_out_dev` != NULL it receives, per sorted slot, the previous index. */
+int gempic_pg_sort(gempic_handle pg, gempic_handle pmc);
+/* Device-side synthetic loads: counter-based RNG, seed 1234 default.
+ * kind 0: x ~ U[0,L), v ~ N(0, sigma_k); kind 1: Landau x by inverse CDF of 1+alpha*cos(kx).
+ * weights = L (1D) ; first_index = global index of this rank's first particle. */
+int gempic_pg_sample(gempic_handle pg, int kind, double xmin, double L, double alpha, double k,
+                     const double *sigma, uint64_t seed, int64_t first_index);
+
+/* ---- ParticleMeshCoupling1D (src/particle_mesh_coupling_1d.jl:26-95) ------------------ */
+int gempic_pmc1d_create(double xmin, double xmax, int n_grid, int64_t no_particles, int spline_degree,
+                        int smoothing_type, gempic_handle *out);
+int gempic_pmc1d_destroy(gempic_handle pmc);
+/* batched add_charge! (:261-280): rho[n_grid] += sum_i deposit(x_i, w_i); host arrays */
+int gempic_pmc1d_add_charge(gempic_handle pmc, const double *x, const double *w, int64_t n, double *rho);
+/* batched evaluate (:438-453): out[i] = field(x_i) */
+int gempic_pmc1d_evaluate(gempic_handle pmc, const double *x, int64_t n, const double *field, double *out);
+/* batched add_current_update_v! with B (:296-376): j += ..., v[i] updated in place */
+int gempic_pmc1d_add_current_update_v(gempic_handle pmc, const double *x_old, const double *x_new,
+                                      const double *w, double qoverm, const double *bfield, double *v,
+                                      int64_t n, double *j);
+/* 1d1v variant without B (:471-529) */
+int gempic_pmc1d_add_current(gempic_handle pmc, const double *x_old, const double *x_new, const double *w,
+                             int64_t n, double *j);
+/* same on a device-resident ParticleGroup: marker charge = charge*w*common_weight (get_charge) */
+int gempic_pmc1d_add_charge_pg(gempic_handle pmc, gempic_handle pg, double *rho);
+int gempic_pmc1d_evaluate_pg(gempic_handle pmc, gempic_handle pg, const double *field, double *out);
+
+/* ---- ParticleMeshCoupling2D (src/particle_mesh_coupling_2d.jl:12-231) ----------------- */
+int gempic_pmc2d_create(double xmin, double xmax, int nx, double ymin, double ymax, int ny,
+                        int spline_degree, int smoothing_type, gempic_handle *out);
+int gempic_pmc2d_destroy(gempic_handle pmc);
+int gempic_pmc2d_add_charge(gempic_handle pmc, const double *x, const double *y, const double *w, int64_t n,
+                            double *rho);
+int gempic_pmc2d_evaluate(gempic_handle pmc, const double *x, const double *y, int64_t n, const double *field,
+                          double *out);
+int gempic_pmc2d_evaluate_multiple(gempic_handle pmc, const double *x, const double *y, int64_t n,
+                                   const double *field1, const double *field2, double *out1, double *out2);
+int gempic_pmc2d_add_charge_pg(gempic_handle pmc, gempic_handle pg, double *rho);
+int gempic_pmc2d_evaluate_pg(gempic_handle pmc, gempic_handle pg, const double *field, double *out);
+
+/* ---- Maxwell1DFEM (src/maxwell_1d_fem.jl:29-177) -------------------------------------- */
+int gempic_maxwell1d_create(double xmin, double xmax, int n_dofs, int degree, gempic_handle *out);
+int gempic_maxwell1d_destroy(gempic_handle m);
+/* which: 0 eig_mass0, 1 eig_mass1, 2 eig_weak_ampere, 3 eig_weak_poisson (FFTW half-complex layout) */
+int gempic_maxwell1d_get_table(gempic_handle m, int which, double *out);
+int gempic_maxwell1d_compute_e_from_rho(gempic_handle m, double *e, const double *rho);          /* :244-255 */
+int gempic_maxwell1d_compute_e_from_j(gempic_handle m, double *e, const double *j, int component); /* :263-289 */
+int gempic_maxwell1d_compute_e_from_b(gempic_handle m, double *e, double dt, const double *b);    /* :384-396 */
+int gempic_maxwell1d_compute_b_from_e(gempic_handle m, double *b, double dt, const double *e);    /* :407-420 */
+int gempic_maxwell1d_inner_product(gempic_handle m, const double *c1, const double *c2, int degree,
+                                   double *out);                                                  /* :461-475 */
+int gempic_maxwell1d_l2norm_squared(gempic_handle m, const double *c, int degree, double *out);   /* :299-313 */
+/* set-up helpers (host quadrature of a C callback, then the device circulant solve) */
+typedef double (*gempic_func1d)(double x, void *ctx);
+int gempic_maxwell1d_compute_rhs_from_function(gempic_handle m, double *coefs, gempic_func1d f, void *ctx,
+                                               int degree);                                       /* :188-220 */
+int gempic_maxwell1d_l2projection(gempic_handle m, double *coefs, gempic_func1d f, void *ctx, int degree); /* :347-374 */
+
+/* ---- HamiltonianSplitting{1,2} / {1,1} (src/hamiltonian_splitting.jl:20-108) ---------- */
+int gempic_hs_create(int D, int V, gempic_handle maxwell, gempic_handle pmc0, gempic_handle pmc1,
+                     gempic_handle pg, gempic_handle *out);
+int gempic_hs_destroy(gempic_handle hs);
+/* e_dofs/b_dofs are aliased caller arrays in the reference (:80-81): copy them in / out. */
+int gempic_hs_set_fields(gempic_handle hs, const double *e1, const double *e2, const double *b);
+int gempic_hs_get_fields(gempic_handle hs, double *e1, double *e2, double *b, double *j1, double *j2);
+/* device-resident calls: asynchronous on gempic_stream() */
+int gempic_hs_operator(gempic_handle hs, int op, double dt);          /* operatorHp1/Hp2/HE/HB */
+int gempic_hs_strang_splitting(gempic_handle hs, double dt, int64_t number_steps);   /* :98-108 */
+/* drop-in calls with HOST field buffers: H2D(e1,e2,b) -> op -> D2H(e1,e2,b,j1,j2) -> sync.
+ * NULL j1/j2 are skipped. */
+int gempic_hs_operator_host(gempic_handle hs, int op, double dt, double *e1, double *e2, double *b,
+                            double *j1, double *j2);
+int gempic_hs_strang_splitting_host(gempic_handle hs, double dt, int64_t number_steps, double *e1, double *e2,
+                                    double *b, double *j1, double *j2);
+/* Same trajectory with the particle passes of a Strang step fused:
+ * fuse = 0 one kernel per reference operator (default), 1 fused [HE,Hp2,Hp1,Hp2] pass. */
+int gempic_hs_set_fusion(gempic_handle hs, int fuse);
+
+/* ---- HamiltonianSplittingBoris (src/hamiltonian_splitting_boris.jl:23-288) ------------ */
+int gempic_boris_create(gempic_handle maxwell, gempic_handle pmc0, gempic_handle pmc1, gempic_handle pg,
+                        gempic_handle *out);
+int gempic_boris_destroy(gempic_handle bs);
+int gempic_boris_set_fields(gempic_handle bs, const double *e1, const double *e2, const double *b);
+/* which = GEMPIC_F_* (E1,E2,B,J1,J2,E1_MID,E2_MID,B_MID) */
+int gempic_boris_get_field(gempic_handle bs, int which, double *out);
+int gempic_boris_staggering(gempic_handle bs, double dt);                              /* :99-122 */
+int gempic_boris_strang_splitting(gempic_handle bs, double dt, int64_t number_steps);  /* :132-177 */
+int gempic_boris_push_v_epart(gempic_handle bs, double dt);                            /* :189-204 */
+int gempic_boris_push_v_bpart(gempic_handle bs, double dt);                            /* :211-233 */
+int gempic_boris_push_x_accumulate_j(gempic_handle bs, double dt);                     /* :250-288 */
+int gempic_boris_staggering_host(gempic_handle bs, double dt, double *e1, double *e2, double *b);
+int gempic_boris_strang_splitting_host(gempic_handle bs, double dt, int64_t number_steps, double *e1,
+                                       double *e2, double *b);
+
+/* ---- diagnostics (src/diagnostics.jl) -------------------------------------------------- */
+/* solve_poisson! (:15-31): rho[n] and efield[n] are host outputs */
+int gempic_solve_poisson(gempic_handle pg, gempic_handle pmc0, gempic_handle maxwell, double *efield,
+                         double *rho);
+/* write_step! (:186-250): out[11] = Time, KineticEnergy, Momentum1, Momentum2, PotentialEnergyE1,
+ * PotentialEnergyE2, PotentialEnergyB3, Transfer, VVB, Poynting, ErrorPoisson (:143-155) */
+int gempic_diag_write_step(gempic_handle pg, gempic_handle maxwell, gempic_handle pmc0, gempic_handle pmc1,
+                           double time, int degree, const double *e1, const double *e2, const double *b,
+                           const double *e1_n, const double *e2_n, const double *e_poisson, double *out11);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEMPIC_B200_H */

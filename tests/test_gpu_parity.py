@@ -1,0 +1,239 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on identical seeded inputs.
+
+Tolerance (BASELINE.json north_star): grid rho/j and particle x/v within 1e-12 relative in fp64;
+atomic / tree summation order is the only permitted difference.  Sizes are chosen so that the
+serial oracle finishes in seconds."""
+import math
+
+import numpy as np
+import pytest
+
+from .helpers import Sim1D, landau_state, particle_err, rel_err, weibel_state
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+L_LANDAU = 4 * math.pi
+L_WEIBEL = 2 * math.pi / 1.25
+
+
+def both(orc, gp, state, L, **kw):
+    return Sim1D(orc, state, L, **kw), Sim1D(gp, state, L, **kw)
+
+
+def check_fields(so, sg, tol=TOL):
+    for name in ("e1", "e2", "b"):
+        assert rel_err(getattr(sg, name), getattr(so, name)) < tol, name
+    for k in range(2):
+        jo, jg = so.h.j_dofs[k], sg.h.j_dofs[k]
+        if np.max(np.abs(jo)) > 0:
+            assert rel_err(jg, jo) < tol, f"j{k + 1}"
+        else:
+            assert np.max(np.abs(jg)) == 0.0
+
+
+@pytest.mark.parametrize("n,nx", [(100_000, 32), (99_999, 32), (50_001, 24), (3, 32), (1, 8)])
+def test_operators_1d2v(orc, gp, n, nx):
+    state = landau_state(n, L_LANDAU, seed=n)
+    so, sg = both(orc, gp, state, L_LANDAU, nx=nx)
+    so.init_fields(), sg.init_fields()
+    assert rel_err(sg.e1, so.e1) < TOL and rel_err(sg.rho, so.rho) < TOL
+    ho, hg = so.splitting(), sg.splitting()
+    for op, dt in (("operatorHB", 0.025), ("operatorHE", 0.025), ("operatorHp2", 0.025), ("operatorHp1", 0.05),
+                   ("operatorHp2", 0.025), ("operatorHE", 0.025), ("operatorHB", 0.025)):
+        getattr(ho, op)(dt)
+        getattr(hg, op)(dt)
+        assert particle_err(sg.particles(), so.particles(), L_LANDAU) < TOL, op
+        check_fields(so, sg)
+
+
+@pytest.mark.parametrize("deg0,deg1", [(3, 2), (3, 3), (2, 1), (2, 2), (1, 0), (1, 1)])
+@pytest.mark.parametrize("smoothing", ["galerkin", "collocation"])
+def test_strang_all_degrees(orc, gp, deg0, deg1, smoothing):
+    n = 40_000
+    state = weibel_state(n, L_WEIBEL, seed=deg0 * 10 + deg1)
+    so, sg = both(orc, gp, state, L_WEIBEL, nx=32, deg0=deg0, deg1=deg1, smoothing=smoothing)
+    so.init_fields(b_amp=1e-2, e2_amp=1e-3), sg.init_fields(b_amp=1e-2, e2_amp=1e-3)
+    ho, hg = so.splitting(), sg.splitting()
+    ho.strang_splitting(0.05, 3)
+    hg.strang_splitting(0.05, 3)
+    assert particle_err(sg.particles(), so.particles(), L_WEIBEL) < 1e-11  # 3 steps of chaotic amplification
+    check_fields(so, sg, tol=1e-11)
+
+
+def test_strang_resident_equals_host_path(orc, gp):
+    n = 30_000
+    state = landau_state(n, L_LANDAU, seed=5)
+    sa, sb = Sim1D(gp, state, L_LANDAU).init_fields(), Sim1D(gp, state, L_LANDAU).init_fields()
+    ha, hb = sa.splitting(), sb.splitting(resident=True)
+    for _ in range(4):
+        ha.strang_splitting(0.05, 1)
+    hb.strang_splitting(0.05, 4)
+    hb.sync_fields()
+    # LANE-mode deposits are deterministic -> the two paths agree bit for bit
+    assert np.array_equal(sa.particles(), sb.particles())
+    for name in ("e1", "e2", "b"):
+        assert np.array_equal(getattr(sa, name), getattr(sb, name))
+
+
+def test_multicell_and_backward_crossings(orc, gp):
+    # fast particles: several cells per step in both directions, x_new < 0 (trunc quirk)
+    n = 20_000
+    state = landau_state(n, L_LANDAU, seed=11, sigma=(12.0, 1.0))
+    so, sg = both(orc, gp, state, L_LANDAU, nx=32)
+    so.init_fields(), sg.init_fields()
+    ho, hg = so.splitting(), sg.splitting()
+    ho.operatorHp1(0.2)
+    hg.operatorHp1(0.2)
+    assert particle_err(sg.particles(), so.particles(), L_LANDAU) < TOL
+    check_fields(so, sg)
+
+
+def test_nonzero_xmin_charge_mass(orc, gp):
+    n = 20_000
+    state = landau_state(n, L_LANDAU, seed=3)
+    state[0] += 1.5
+    kw = dict(nx=16, xmin=1.5, charge=-1.0, mass=2.0, common_weight=0.37 / n)
+    so, sg = both(orc, gp, state, L_LANDAU, **kw)
+    so.init_fields(), sg.init_fields()
+    ho, hg = so.splitting(), sg.splitting()
+    # NB: the reference wraps with mod(x_new, Lx) ignoring xmin -- reproduced
+    ho.strang_splitting(0.05, 1)
+    hg.strang_splitting(0.05, 1)
+    assert particle_err(sg.particles(), so.particles(), L_LANDAU) < TOL
+    check_fields(so, sg)
+
+
+def test_large_grid_uses_atomic_mode(orc, gp):
+    # 512 cells: lane-private copies no longer fit -> shared-memory atomics path
+    n = 60_000
+    state = landau_state(n, L_LANDAU, seed=8)
+    so, sg = both(orc, gp, state, L_LANDAU, nx=512)
+    so.init_fields(), sg.init_fields()
+    ho, hg = so.splitting(), sg.splitting()
+    ho.strang_splitting(0.05, 1)
+    hg.strang_splitting(0.05, 1)
+    assert particle_err(sg.particles(), so.particles(), L_LANDAU) < TOL
+    check_fields(so, sg, tol=1e-11)
+
+
+def test_1d1v(orc, gp):
+    # config 1: strong Landau damping 1d1v (examples/strong_landau_damping_1d1v.jl), N = 1e5
+    n = 100_000
+    state = landau_state(n, L_LANDAU, seed=1234, V=1)
+    so, sg = both(orc, gp, state, L_LANDAU, nx=32, V=1)
+    so.init_fields(b_amp=0.0), sg.init_fields(b_amp=0.0)
+    ho, hg = so.splitting(V=1), sg.splitting(V=1)
+    ho.operatorHB(0.025), hg.operatorHB(0.025)
+    assert particle_err(sg.particles(), so.particles(), L_LANDAU) < TOL
+    ho.operatorHp1(0.05), hg.operatorHp1(0.05)
+    assert particle_err(sg.particles(), so.particles(), L_LANDAU) < TOL
+    check_fields(so, sg)
+    ho.strang_splitting(0.05, 5), hg.strang_splitting(0.05, 5)
+    assert particle_err(sg.particles(), so.particles(), L_LANDAU) < 1e-11
+    assert rel_err(sg.e1, so.e1) < 1e-11
+
+
+def test_boris(orc, gp):
+    n = 80_000
+    state = landau_state(n, L_LANDAU, seed=21)
+    so, sg = both(orc, gp, state, L_LANDAU, nx=32)
+    so.init_fields(b_amp=5e-2, e2_amp=1e-2), sg.init_fields(b_amp=5e-2, e2_amp=1e-2)
+    bo, bg = so.boris(), sg.boris()
+    bo.staggering(0.05), bg.staggering(0.05)
+    assert particle_err(sg.particles(), so.particles(), L_LANDAU) < TOL
+    for k in range(2):
+        assert rel_err(bg.e_dofs_mid[k], bo.e_dofs_mid[k]) < TOL
+        assert rel_err(bg.j_dofs[k], bo.j_dofs[k]) < TOL
+    bo.strang_splitting(0.05, 2), bg.strang_splitting(0.05, 2)
+    assert particle_err(sg.particles(), so.particles(), L_LANDAU) < 1e-11
+    for name in ("e1", "e2", "b"):
+        assert rel_err(getattr(sg, name), getattr(so, name)) < 1e-11, name
+    for k in range(2):
+        assert rel_err(bg.e_dofs_mid[k], bo.e_dofs_mid[k]) < 1e-11
+    assert rel_err(bg.b_dofs_mid, bo.b_dofs_mid) < 1e-11
+    # the individual pushes (same entry points the reference exposes)
+    for name, dt in (("push_v_epart", 0.025), ("push_v_bpart", 0.05), ("push_x_accumulate_j", 0.05)):
+        getattr(bo, name)(dt), getattr(bg, name)(dt)
+        assert particle_err(sg.particles(), so.particles(), L_LANDAU) < 1e-11, name
+    for k in range(2):
+        assert rel_err(bg.j_dofs[k], bo.j_dofs[k]) < 1e-11
+
+
+def test_diagnostics_write_step(orc, gp):
+    n = 50_000
+    state = weibel_state(n, L_WEIBEL, seed=2)
+    so, sg = both(orc, gp, state, L_WEIBEL, nx=32)
+    so.init_fields(b_amp=1e-2, e2_amp=1e-3), sg.init_fields(b_amp=1e-2, e2_amp=1e-3)
+    ho, hg = so.splitting(), sg.splitting()
+    ho.strang_splitting(0.05, 2), hg.strang_splitting(0.05, 2)
+    epo, epg, rho_o, rho_g = np.zeros(32), np.zeros(32), np.zeros(32), np.zeros(32)
+    orc.solve_poisson(epo, so.pg, so.ks0, so.mx, rho_o)
+    gp.solve_poisson(epg, sg.pg, sg.ks0, sg.mx, rho_g)
+    assert rel_err(rho_g, rho_o) < TOL and rel_err(epg, epo) < 1e-11
+    ref = orc.write_step(so.pg, so.mx, so.ks0, so.ks1, 0.1, 3, [so.e1, so.e2], so.b, [so.e1, so.e2], epo)
+    th = gp.TimeHistoryDiagnostics(sg.pg, sg.mx, sg.ks0, sg.ks1)
+    got = gp.write_step(th, 0.1, 3, [sg.e1, sg.e2], sg.b, [sg.e1, sg.e2], epg)
+    assert got[0] == 0.1
+    for k, name in enumerate(gp.DIAG_COLUMNS):
+        if name in ("Time",):
+            continue
+        scale = max(abs(ref[k]), 1e-12 if name in ("Momentum1", "Momentum2", "Transfer", "VVB", "Poynting", "ErrorPoisson") else 0)
+        assert abs(got[k] - ref[k]) <= 1e-10 * max(scale, abs(ref[1]) * 1e-6), (name, got[k], ref[k])
+
+
+def test_sort_keeps_physics(orc, gp):
+    n = 70_001
+    state = landau_state(n, L_LANDAU, seed=13)
+    sa, sb = Sim1D(gp, state, L_LANDAU).init_fields(), Sim1D(gp, state, L_LANDAU).init_fields()
+    sb.pg.sort(sb.ks0)
+    srt = sb.particles()
+    cells = np.floor(srt[0] / (L_LANDAU / 32)).astype(int) % 32
+    assert np.all(np.diff(cells) >= 0), "particles are not cell-sorted"
+    # stable sort == numpy's stable argsort of the same keys
+    cells0 = np.trunc(state[0] / (L_LANDAU / 32)).astype(int) % 32
+    perm = np.argsort(cells0, kind="stable")
+    assert np.array_equal(srt, state[:, perm])
+    ha, hb = sa.splitting(), sb.splitting()
+    ha.strang_splitting(0.05, 2), hb.strang_splitting(0.05, 2)
+    for name in ("e1", "e2", "b"):
+        assert rel_err(getattr(sb, name), getattr(sa, name)) < 1e-11, name
+    pa, pb = sa.particles(), sb.particles()
+    assert particle_err(pb, pa[:, perm], L_LANDAU) < 1e-11
+
+
+def test_pmc2d_random(orc, gp):
+    rng = np.random.default_rng(4)
+    n = 20_000
+    grid_o = orc.TwoDGrid(0.0, 4 * math.pi, 64, -1.0, 2.0, 48)
+    grid_g = gp.TwoDGrid(0.0, 4 * math.pi, 64, -1.0, 2.0, 48)
+    x, y, w = rng.uniform(0, 4 * math.pi, n), rng.uniform(-1.0, 2.0, n), rng.uniform(0.5, 1.5, n)
+    for deg in (1, 2, 3):
+        for smoothing in ("galerkin", "collocation"):
+            ko = orc.ParticleMeshCoupling2D(grid_o, deg, smoothing)
+            kg = gp.ParticleMeshCoupling2D(None, grid_g, deg, smoothing)
+            ro, rg = np.zeros(64 * 48), np.zeros(64 * 48)
+            ko.add_charge_batch(ro, x, y, w)
+            kg.add_charge(rg, x, y, w)
+            assert rel_err(rg, ro) < TOL
+            fo = ko.evaluate_batch(x, y, ro)
+            fg = kg.evaluate(x, y, ro)
+            assert rel_err(fg, fo) < TOL
+
+
+def test_device_sampler_statistics(gp):
+    # statistical counterpart of test/test_sampling.jl: mean / variance of the synthetic loads
+    n = 400_000
+    pg = gp.ParticleGroup(1, 2, n)
+    pg.sample("landau", 0.0, L_LANDAU, alpha=0.5, k=0.5, sigma=(1.0, 2.0), seed=1234)
+    a = pg.to_host()
+    assert a[0].min() >= 0 and a[0].max() < L_LANDAU
+    assert abs(a[1].mean()) < 1e-2 and abs(a[1].var() - 1.0) < 2e-2
+    assert abs(a[2].mean()) < 2e-2 and abs(a[2].var() - 4.0) < 6e-2
+    assert np.all(a[3] == L_LANDAU)
+    # first Fourier mode of the density: <cos(kx)> = alpha/2
+    assert abs(np.cos(0.5 * a[0]).mean() - 0.25) < 5e-3
+    # sharding invariance: ranks sampling disjoint index ranges reproduce the single-rank load
+    pg2 = gp.ParticleGroup(1, 2, n // 2)
+    pg2.sample("landau", 0.0, L_LANDAU, alpha=0.5, k=0.5, sigma=(1.0, 2.0), seed=1234, first_index=n // 2)
+    assert np.array_equal(pg2.to_host(), a[:, n // 2:])
