@@ -46,7 +46,9 @@ BETA = 1e-4
 NX = 32
 DT = 0.05
 DEG = 3
-BYTES = {"operatorHE": 40, "operatorHp2": 40, "operatorHp1": 48, "strang_step": 208}
+# algorithmic DRAM bytes per particle of each pass (fp64 SoA rows x, v1, v2, w; SURVEY section 8d / DESIGN.md)
+BYTES = {"operatorHE": 40, "operatorHp2": 40, "operatorHp1": 48, "strang_step": 208,
+         "fused[HE,Hp2,Hp1,Hp2]": 56, "fused[HE,HE,Hp2,Hp1,Hp2]": 56}
 
 
 def peaks():
@@ -175,7 +177,8 @@ def workload_config(args, n_per_gpu, note=None):
            "particles_per_gpu": int(n_per_gpu), "n_cells": NX, "spline_degree": [DEG, DEG - 1], "dt": DT,
            "parallelism": f"particles sharded over {args.gpus} GPU(s), NCCL allreduce of rho/j",
            "l2_policy": "inputs (32 B/particle x N >> 126 MB L2) stream from HBM every pass; no flush needed",
-           "kernels": "fused" if args.fuse else "one pass per reference operator"}
+           "kernels": ("fused passes [HE,(HE,)Hp2,Hp1,Hp2] + HE, one strang_splitting!(h, dt, K) call" if args.fuse
+                       else "one pass per reference operator, K calls of strang_splitting!(h, dt, 1)")}
     if note:
         cfg["note"] = note
     return cfg
@@ -231,6 +234,8 @@ def run_ours(args):
         return dc.max_over_ranks(ev0.elapsed_time(ev1))   # ms, max over ranks
 
     # ---- value: device-resident -------------------------------------------------------------
+    # fused: one strang_splitting!(h, dt, K) call (the trailing HE of a step rides in the next step's pass);
+    # unfused: K calls of one step, one kernel per reference operator
     step = lambda: h.strang_splitting(DT, 1)
     for _ in range(args.warmup):
         step()
@@ -241,7 +246,10 @@ def run_ours(args):
     _lib = sys.modules["gempic_jl_b200._lib"]
     _lib.check(L.gempic_profile_enable(C.c_int(1)))
     gp.launch_count(reset=True)
-    ms = timed(step, args.steps)
+    if args.fuse:
+        ms = timed(lambda: h.strang_splitting(DT, args.steps), 1)
+    else:
+        ms = timed(step, args.steps)
     launches = gp.launch_count()
     prof = {}
     slot = 0
@@ -284,12 +292,12 @@ def run_ours(args):
 
     if dc.rank == 0:
         peak, peak_src = peaks()
-        dom = "operatorHp1"
+        dom = max(prof, key=lambda k: prof[k][0]) if prof else None   # the pass with the largest share of the step
         roof = None
         if dom in prof and prof[dom][1] > 0:
             t_ms = prof[dom][0] / prof[dom][1]
             achieved = BYTES[dom] * n_local / (t_ms * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": "k_pass<OpHp1<3,2,false>> (operatorHp1 pass)", "achieved": achieved,
+            roof = {"bound": "hbm", "kernel": f"k_pass<{dom}>", "achieved": achieved,
                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_particle": BYTES[dom], "avg_launch_ms": t_ms,
                     "all_passes": {k: {"avg_ms": v[0] / max(v[1], 1), "launches": v[1],
@@ -326,7 +334,7 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=4_000_000, help="bounded sample for the CPU arm")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--fuse", type=int, default=0)
+    ap.add_argument("--fuse", type=int, default=1, help="1: fused particle passes (default), 0: one kernel per reference operator")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3   # timing rule: W >= 3

@@ -504,7 +504,7 @@ int gempic_hs_create(int D, int V, gempic_handle maxwell, gempic_handle pmc0, ge
     GP_REQUIRE(h->ks0->xmin == h->ks1->xmin && h->ks0->xmax == h->ks1->xmax, GEMPIC_EINVAL,
                "both kernel smoothers must live on the same mesh");
     h->D = D; h->V = V; h->n = h->ks0->n_grid;
-    h->fields.alloc((size_t)7 * h->n);
+    h->fields.alloc((size_t)10 * h->n);
     h->fields.zero(ctx().stream);
     *out = register_object(std::move(h));
     GP_API_END

@@ -48,8 +48,8 @@ void boris_push_x_accumulate_j(Boris &s, double dt)   // :250-288
     GP_DISPATCH_DEGREES(s.ks0->degree, s.ks1->degree, {
         using Op = OpBorisX<D0, D1>;
         auto P = base_params<Op>(s);
-        P.n_acc = 2 * s.n;
-        P.op = {dt, s.pg->charge, s.pg->common_weight, s.ks0->scaling, s.ks1->scaling};
+        const double cq = s.pg->charge * s.pg->common_weight;
+        P.op = {dt, cq * s.ks0->scaling, cq * s.ks1->scaling};
         launch_pass<Op>(P, &s.scratch, s.f(GEMPIC_F_J1), "push_x_accumulate_j");   // j1 | j2 adjacent
     });
     allreduce_sum(s.f(GEMPIC_F_J1), 2 * s.n);
@@ -86,9 +86,8 @@ static void boris_step(Boris &s, double dt)   // :132-177
         P.fields[0] = s.f(GEMPIC_F_E1_MID);
         P.fields[1] = s.f(GEMPIC_F_E2_MID);
         P.fields[2] = s.f(GEMPIC_F_B_MID);
-        P.n_acc = 2 * s.n;
-        P.op = {dt, (0.5 * dt) * s.pg->q_over_m, s.pg->q_over_m * 0.5 * dt, s.pg->charge, s.pg->common_weight,
-                s.ks0->scaling, s.ks1->scaling};
+        const double cq = s.pg->charge * s.pg->common_weight;
+        P.op = {dt, (0.5 * dt) * s.pg->q_over_m, s.pg->q_over_m * 0.5 * dt, cq * s.ks0->scaling, cq * s.ks1->scaling};
         launch_pass<Op>(P, &s.scratch, s.f(GEMPIC_F_J1), "boris_step");
     });
     allreduce_sum(s.f(GEMPIC_F_J1), 2 * s.n);

@@ -16,24 +16,28 @@ static PassParams<Op> base_params(Splitting &h)
     P.r = h.pg->rows1d();
     P.n_particles = h.pg->n;
     P.m = h.mesh();
-    P.n_acc = 0;
     P.copies = 0;
     P.partials = nullptr;
     return P;
 }
 
 // ---- {1,2} ----------------------------------------------------------------------------
-static void op_HE(Splitting &h, double dt)
+static void op_HE_particles(Splitting &h, double dt, const double *e1, const double *e2)
 {
     const double dtqm = dt * h.pg->q_over_m;
     GP_DISPATCH_DEGREES(h.ks0->degree, h.ks1->degree, {
         using Op = OpHE<D0, D1>;
         auto P = base_params<Op>(h);
-        P.fields[0] = h.e1();
-        P.fields[1] = h.e2();
+        P.fields[0] = e1;
+        P.fields[1] = e2;
         P.op.dtqm = dtqm;
         launch_pass<Op>(P, &h.scratch, nullptr, "operatorHE");
     });
+}
+
+static void op_HE(Splitting &h, double dt)
+{
+    op_HE_particles(h, dt, h.e1(), h.e2());
     field_b_from_e(*h.maxwell, h.b(), dt, h.e2());   // :218
 }
 
@@ -46,16 +50,23 @@ static void op_Hp2(Splitting &h, double dt)
         using Op = OpHp2<D0, D1>;
         auto P = base_params<Op>(h);
         P.fields[0] = h.b();
-        P.n_acc = h.n;
         P.op.dtqm = dtqm;
-        P.op.charge = h.pg->charge;
-        P.op.cw = h.pg->common_weight;
-        P.op.scaling0 = h.ks0->scaling;
+        P.op.wscale0 = h.pg->charge * h.pg->common_weight * h.ks0->scaling;
         launch_pass<Op>(P, &h.scratch, h.j2(), "operatorHp2");
     });
     GP_CUDA(cudaMemsetAsync(h.j1(), 0, sizeof(double) * h.n, ctx().stream));   // fill!(j_dofs[1], 0) :132
     allreduce_sum(h.j2(), h.n);
     field_e_from_j(*h.maxwell, h.e2(), h.j2(), 2, dt);   // j2 .*= dt ; compute_e_from_j!(e2, j2, 2)  :173-175
+}
+
+template <class Op>
+static void set_hp1_params(Splitting &h, double dt, typename Op::Params &op)
+{
+    const double cq = h.pg->charge * h.pg->common_weight;
+    op.dt = dt;
+    op.qm_dx = h.pg->q_over_m * h.ks1->delta_x;
+    op.wscale0 = cq * h.ks0->scaling;
+    op.wscale1_dx = cq * h.ks1->scaling * h.ks1->delta_x;
 }
 
 static void op_Hp1(Splitting &h, double dt, bool with_rho)
@@ -65,20 +76,92 @@ static void op_Hp1(Splitting &h, double dt, bool with_rho)
             using Op = OpHp1<D0, D1, true>;
             auto P = base_params<Op>(h);
             P.fields[0] = h.b();
-            P.n_acc = 2 * h.n;
-            P.op = {dt, h.pg->q_over_m, h.pg->charge, h.pg->common_weight, h.ks0->scaling, h.ks1->scaling};
-            launch_pass<Op>(P, &h.scratch, h.j1(), "operatorHp1+rho");   // j1 | j2 are adjacent: acc = [j1, rho]
+            set_hp1_params<Op>(h, dt, P.op);
+            launch_pass<Op>(P, &h.scratch, h.j1(), "operatorHp1+rho");   // j1 | j2 are adjacent: out = [j1, rho]
         } else {
             using Op = OpHp1<D0, D1, false>;
             auto P = base_params<Op>(h);
             P.fields[0] = h.b();
-            P.n_acc = h.n;
-            P.op = {dt, h.pg->q_over_m, h.pg->charge, h.pg->common_weight, h.ks0->scaling, h.ks1->scaling};
+            set_hp1_params<Op>(h, dt, P.op);
             launch_pass<Op>(P, &h.scratch, h.j1(), "operatorHp1");
         }
     });
     allreduce_sum(h.j1(), with_rho ? 2 * h.n : h.n);
     field_e_from_j(*h.maxwell, h.e1(), h.j1(), 1, 1.0);   // :111
+}
+
+// fused particle pass [HE x n_he, Hp2(dt/2), Hp1(dt), Hp2(dt/2)] + the three field solves.
+// n_he = 1: fields e1,e2 = current.  n_he = 2: the first kick reads the snapshot (e1T, e2T)
+// taken before the trailing HE's field update of the previous step.
+static void fused_pass(Splitting &h, double dt, int n_he)
+{
+    const double qm = h.pg->q_over_m;
+    GP_DISPATCH_DEGREES(h.ks0->degree, h.ks1->degree, {
+        if (n_he == 1) {
+            using Op = OpStrangFused<D0, D1, 1>;
+            auto P = base_params<Op>(h);
+            P.fields[0] = h.e1();
+            P.fields[1] = h.e2();
+            P.fields[2] = h.b();
+            P.op.dtqm_e[0] = P.op.dtqm_e[1] = 0.5 * dt * qm;
+            P.op.dtqm_p2 = 0.5 * dt * qm;
+            typename OpHp1<D0, D1, false>::Params hp;
+            set_hp1_params<OpHp1<D0, D1, false>>(h, dt, hp);
+            P.op.dt = hp.dt; P.op.qm_dx = hp.qm_dx; P.op.wscale0 = hp.wscale0; P.op.wscale1_dx = hp.wscale1_dx;
+            launch_pass<Op>(P, &h.scratch, h.acc(), "fused[HE,Hp2,Hp1,Hp2]");
+        } else {
+            using Op = OpStrangFused<D0, D1, 2>;
+            auto P = base_params<Op>(h);
+            P.fields[0] = h.e1T();
+            P.fields[1] = h.e2T();
+            P.fields[2] = h.e1();
+            P.fields[3] = h.e2();
+            P.fields[4] = h.b();
+            P.op.dtqm_e[0] = P.op.dtqm_e[1] = 0.5 * dt * qm;
+            P.op.dtqm_p2 = 0.5 * dt * qm;
+            typename OpHp1<D0, D1, false>::Params hp;
+            set_hp1_params<OpHp1<D0, D1, false>>(h, dt, hp);
+            P.op.dt = hp.dt; P.op.qm_dx = hp.qm_dx; P.op.wscale0 = hp.wscale0; P.op.wscale1_dx = hp.wscale1_dx;
+            launch_pass<Op>(P, &h.scratch, h.acc(), "fused[HE,HE,Hp2,Hp1,Hp2]");
+        }
+    });
+    allreduce_sum(h.acc(), 3 * h.n);
+    const Maxwell1D &m = *h.maxwell;
+    field_e_from_j(m, h.e2(), h.acc(), 2, 0.5 * dt);             // first Hp2   :173-175
+    field_e_from_j(m, h.e1(), h.acc() + h.n, 1, 1.0);            // Hp1         :111
+    field_e_from_j(m, h.e2(), h.acc() + 2 * h.n, 2, 0.5 * dt);   // second Hp2
+    // j_dofs as the reference leaves them: the last Hp2 zeroed j1 (:132) and holds dt/2 * j2
+    GP_CUDA(cudaMemsetAsync(h.j1(), 0, sizeof(double) * h.n, ctx().stream));
+    field_copy(h.j2(), h.acc() + 2 * h.n, h.n);
+}
+
+// strang_splitting! (hamiltonian_splitting.jl:98-108) with the particle passes fused.
+// Per step the reference runs HB HE Hp2 Hp1 Hp2 HE HB (each dt/2 except Hp1).  Field-only work
+// is hoisted around two kinds of particle pass:
+//   first step      HB ; [b_from_e] ; fused{HE,Hp2,Hp1,Hp2}
+//   between steps   snapshot eT=(e1,e2) ; b_from_e ; HB ; HB ; [b_from_e] ; fused{HE(eT),HE,Hp2,Hp1,Hp2}
+//   last step       HE pass ; b_from_e ; HB
+// compute_b_from_e! of the leading HE only reads e2 (which the kick also reads) and writes b
+// (which the kick does not read), so b is simply advanced before the pass.
+static void strang_fused(Splitting &h, double dt, int64_t steps)
+{
+    const Maxwell1D &m = *h.maxwell;
+    for (int64_t s = 0; s < steps; ++s) {
+        if (s == 0) {
+            op_HB(h, 0.5 * dt);
+            field_b_from_e(m, h.b(), 0.5 * dt, h.e2());
+            fused_pass(h, dt, 1);
+        } else {
+            field_copy(h.e1T(), h.e1(), 2 * h.n);            // e1T|e2T <- e1|e2 (adjacent)
+            field_b_from_e(m, h.b(), 0.5 * dt, h.e2());      // trailing HE of step s-1, field part
+            op_HB(h, 0.5 * dt);                              // trailing HB of step s-1
+            op_HB(h, 0.5 * dt);                              // leading HB of step s
+            field_b_from_e(m, h.b(), 0.5 * dt, h.e2());      // leading HE of step s, field part
+            fused_pass(h, dt, 2);
+        }
+    }
+    op_HE(h, 0.5 * dt);
+    op_HB(h, 0.5 * dt);
 }
 
 // ---- {1,1} ----------------------------------------------------------------------------
@@ -98,8 +181,7 @@ static void op_Hp111(Splitting &h, double dt)
     GP_DISPATCH_DEGREE(h.ks1->degree, {
         using Op = OpHp111<D>;
         auto P = base_params<Op>(h);
-        P.n_acc = h.n;
-        P.op = {dt, h.pg->charge, h.pg->common_weight, h.ks1->scaling};
+        P.op = {dt, h.pg->charge * h.pg->common_weight * h.ks1->scaling * h.ks1->delta_x};
         launch_pass<Op>(P, &h.scratch, h.j1(), "operatorHp1{1,1}");
     });
     GP_CUDA(cudaMemsetAsync(h.j2(), 0, sizeof(double) * h.n, ctx().stream));   // fill!(j_dofs[2], 0) 1d1v.jl:68
@@ -145,6 +227,11 @@ static void strang_step(Splitting &h, double dt)
 
 void hs_strang(Splitting &h, double dt, int64_t steps)
 {
+    if (steps <= 0) return;
+    if (h.fuse && h.V == 2) {
+        strang_fused(h, dt, steps);
+        return;
+    }
     for (int64_t s = 0; s < steps; ++s) strang_step(h, dt);
 }
 

@@ -16,7 +16,7 @@ struct PartialScratch {
 
 // LANE mode is used while one block's private copies stay below this many bytes, which
 // keeps >= 2 blocks (8 warps) resident per SM.
-constexpr size_t kLanePrivateMaxBytes = 100 * 1024;
+constexpr size_t kLanePrivateMaxBytes = 110 * 1024;
 constexpr size_t kSmemBudget = 200 * 1024;
 
 struct LaunchInfo {
@@ -30,20 +30,20 @@ template <class Op>
 inline LaunchInfo plan_pass(const PassParams<Op> &P)
 {
     LaunchInfo L;
-    const size_t field_bytes = (size_t)Op::NF * P.m.n * sizeof(double);
+    const size_t field_bytes = (size_t)Op::NF * (P.m.n + kHalo) * sizeof(double);
     if (!Op::DEPOSIT) {
         L.lane_private = true;
         L.smem = field_bytes;
         return L;
     }
-    const size_t lp = (size_t)P.n_acc * 32 * kWarps * sizeof(double);
-    if (lp <= kLanePrivateMaxBytes) {
+    const size_t one = (size_t)acc_slots<Op>(P.m.n) * sizeof(double);
+    const size_t lp = one * 32 * kWarps;
+    if (field_bytes + lp <= kLanePrivateMaxBytes) {
         L.lane_private = true;
         L.smem = field_bytes + lp;
     } else {
-        const size_t one = (size_t)P.n_acc * sizeof(double);
         GP_REQUIRE(field_bytes + one <= kSmemBudget, GEMPIC_EINVAL,
-                   "deposit grid of %d dofs does not fit in shared memory", P.n_acc);
+                   "deposit grid of %d dofs does not fit in shared memory", acc_outputs<Op>(P.m.n));
         size_t copies = (kSmemBudget / 2 - field_bytes) / one;
         if (copies < 1) copies = 1;
         if (copies > (size_t)kWarps) copies = kWarps;
@@ -74,8 +74,9 @@ template <class Op>
 inline void launch_pass(PassParams<Op> P, PartialScratch *scratch, double *out, const char *tag = nullptr)
 {
     Context &c = ctx();
+    const int n_out = acc_outputs<Op>(P.m.n);
     if (P.n_particles <= 0) {
-        if (Op::DEPOSIT && out) GP_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * P.n_acc, c.stream));
+        if (Op::DEPOSIT && out) GP_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * n_out, c.stream));
         return;
     }
     LaunchInfo L = plan_pass(P);
@@ -86,7 +87,7 @@ inline void launch_pass(PassParams<Op> P, PartialScratch *scratch, double *out, 
     const int64_t need = (pairs + kBlock - 1) / kBlock;
     if (need < grid) grid = (int)need;
     P.copies = L.copies;
-    if (Op::DEPOSIT) P.partials = scratch->ensure((size_t)grid * P.n_acc);
+    if (Op::DEPOSIT) P.partials = scratch->ensure((size_t)grid * n_out);
     if (tag) profile_begin(tag);
     if (L.lane_private)
         k_pass<Op, true><<<grid, kBlock, L.smem, c.stream>>>(P);
@@ -97,8 +98,8 @@ inline void launch_pass(PassParams<Op> P, PartialScratch *scratch, double *out, 
     count_launch();
     if (Op::DEPOSIT) {
         const int warps_per_block = 4;
-        const int blocks = (P.n_acc + warps_per_block - 1) / warps_per_block;
-        k_reduce_partials<<<blocks, warps_per_block * 32, 0, c.stream>>>(P.partials, grid, P.n_acc, out);
+        const int blocks = (n_out + warps_per_block - 1) / warps_per_block;
+        k_reduce_partials<<<blocks, warps_per_block * 32, 0, c.stream>>>(P.partials, grid, n_out, out);
         GP_CUDA(cudaGetLastError());
         count_launch();
     }

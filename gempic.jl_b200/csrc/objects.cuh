@@ -43,6 +43,7 @@ struct Pmc1D : Object {
         Mesh1D m;
         m.xmin = xmin;
         m.dx = delta_x;
+        m.inv_dx = 1.0 / delta_x;
         m.Lx = Lmod;
         m.n = n_grid;
         m.pow2 = (n_grid & (n_grid - 1)) == 0;
@@ -89,7 +90,7 @@ struct Splitting : Object {
     Pmc1D *ks0, *ks1;
     ParticleGroup *pg;
     int n;
-    DevBuf<double> fields;  // e1, e2, b, j1, j2, acc(2n)   (7 * n)
+    DevBuf<double> fields;  // e1, e2, b, j1, j2, acc(3n), e1T, e2T   (10 * n)
     PartialScratch scratch;
     int fuse = 0;
     // CUDA graph of one Strang step, keyed by dt
@@ -108,6 +109,8 @@ struct Splitting : Object {
     double *j1() { return fields.p + 3 * (size_t)n; }
     double *j2() { return fields.p + 4 * (size_t)n; }
     double *acc() { return fields.p + 5 * (size_t)n; }
+    double *e1T() { return fields.p + 8 * (size_t)n; }
+    double *e2T() { return fields.p + 9 * (size_t)n; }
     Mesh1D mesh() const { return ks0->mesh(maxwell->Lx); }
 };
 

@@ -3,86 +3,125 @@
 // Template parameters D0 / D1 are the spline degrees of kernel_smoother_0 / kernel_smoother_1
 // (src/hamiltonian_splitting.jl:23-24): e2, j2 and rho live on degree D0, e1, b and j1 on
 // degree D1 (src/hamiltonian_splitting_1d2v.jl:70,102,151,163,207-208).
+//
+// Shared-memory fields and accumulator grids carry a periodic halo of kHalo dofs (pass.cuh),
+// so a particle in cell c touches the contiguous slots g0 .. g0+D with g0 = (c-D) mod n.
 #pragma once
 #include "pass.cuh"
 
 namespace gempic {
 
-// rho[(cell-D+k) mod n] += (w * N_k(t)) * scaling        (add_charge!, pmc1d.jl:261-280)
+// Position of a particle on the mesh: cell, in-cell offset and the first dof of a degree-D
+// stencil.  first<D>() wraps once; first<D-1>() follows from it with one compare.
+struct Pos {
+    int c;
+    double t;
+};
+__device__ __forceinline__ Pos locate(double x, const Mesh1D &m)
+{
+    Pos p;
+    cell_offset(x, m, p.c, p.t);
+    return p;
+}
+template <int D>
+__device__ __forceinline__ int first_dof(const Pos &p, const Mesh1D &m)
+{
+    return wrap_index(p.c - D, m);
+}
+
+// sum_k field[g0+k] * b[k], accumulated from 0.0 in k order (evaluate, pmc1d.jl:446-450)
+template <int D>
+__device__ __forceinline__ double gather_h(const double *__restrict__ field, int g0, const double (&b)[D + 1])
+{
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k <= D; ++k) v = fma(field[g0 + k], b[k], v);
+    return v;
+}
+
+// grid[g0+k] += ws * N_k   with ws = marker charge * scaling   (add_charge!, pmc1d.jl:261-280)
 template <int D, bool LP>
-__device__ __forceinline__ void deposit(const Acc<LP> &acc, int goff, int cell, const double (&b)[D + 1], double w,
-                                        double scaling, const Mesh1D &m)
+__device__ __forceinline__ void deposit_h(const Acc<LP> &acc, int slot0, const double (&b)[D + 1], double ws)
 {
-    int g = wrap_index(cell - D, m);
 #pragma unroll
-    for (int k = 0; k <= D; ++k) {
-        acc.add(goff + g, w * b[k] * scaling);
-        g = wrap_next(g + 1, m.n);
-    }
+    for (int k = 0; k <= D; ++k) acc.add(slot0 + k, ws * b[k]);
 }
 
-// one in-cell segment of the current line integral (update_jv!, pmc1d.jl:385-425 / :538-580)
+// add_current_update_v! (pmc1d.jl:296-376, pp arithmetic of :131-230).
+// Line integral of the degree-D splines along x_old -> x_new (un-wrapped), split at cell
+// boundaries.  With P = prim_pp the per-cell weights are
+//     same cell         cell_old:  P(r_new) - P(r_old)
+//     forward crossing  cell_old:  P(1) - P(r_old)      cell_new:  P(r_new)        interior: P(1)
+//     backward crossing cell_old:      - P(r_old)       cell_new:  P(r_new) - P(1) interior: -P(1)
+// all times dx; j[dof] += w*scaling*weight and v -= q/m * weight * B[dof]  (:416-422).
+// P(r_old), P(r_new) are evaluated once by every lane; only the extra deposits of crossing
+// particles diverge.  `pn` is the position of x_new (trunc, or floor for the 1d1v form :487).
 template <int D, bool LP, bool WITH_B>
-__device__ __forceinline__ double update_jv(const Acc<LP> &acc, const double *__restrict__ bfield, double lower,
-                                            double upper, int cell, double w, double qm, double sign_dx,
-                                            double scaling, double vi, const Mesh1D &m)
+__device__ __forceinline__ double current_update_v(const Acc<LP> &acc, int slot_base, const double *__restrict__ bfield,
+                                                   const Pos &po, const Pos &pn, double ws_dx, double qm_dx, double vi,
+                                                   const Mesh1D &m)
 {
-    double s[D + 1];
-    segment_weights<D>(lower, upper, sign_dx, s);
-    int g = wrap_index(cell - D, m);
+    double A[D + 1], B[D + 1];
+    prim_pp<D>(po.t, A);
+    prim_pp<D>(pn.t, B);
+    const bool same = po.c == pn.c, fwd = po.c < pn.c;
+    const int g_old = first_dof<D>(po, m);
+    double bsum = 0.0;
 #pragma unroll
     for (int k = 0; k <= D; ++k) {
-        acc.add(g, w * s[k] * scaling);
-        if (WITH_B) vi = vi - qm * s[k] * bfield[g];
-        g = wrap_next(g + 1, m.n);
+        const double e = same ? B[k] : (fwd ? prim_full<D>(k) : 0.0);
+        const double s = e - A[k];
+        acc.add(slot_base + g_old + k, ws_dx * s);
+        if (WITH_B) bsum = fma(s, bfield[g_old + k], bsum);
     }
-    return vi;
-}
-
-// add_current_update_v! (pmc1d.jl:296-376); NEW_FLOOR selects the 1d1v variant (:471-529)
-// whose new index uses floor (:487).  Segment order is the reference's: all lanes run
-// segment A together, crossing lanes then run B, multi-cell crossers (rare) the loop.
-template <int D, bool LP, bool WITH_B, bool NEW_FLOOR>
-__device__ __forceinline__ double add_current_update_v(const Acc<LP> &acc, const double *__restrict__ bfield,
-                                                       double x_old, double x_new, double w, double qm,
-                                                       double scaling, double vi, const Mesh1D &m)
-{
-    int i_old, i_new;
-    double r_old, r_new;
-    cell_offset(x_old, m, i_old, r_old);
-    if (NEW_FLOOR) {
-        const double xi = (x_new - m.xmin) / m.dx;
-        i_new = __double2int_rd(xi);
-        r_new = xi - (double)i_new;
-    } else {
-        cell_offset(x_new, m, i_new, r_new);
-    }
-    double lo, up, sgn;
-    int cell;
-    if (i_old == i_new) {
-        const bool fwd = r_old < r_new;
-        lo = fwd ? r_old : r_new;
-        up = fwd ? r_new : r_old;
-        sgn = fwd ? m.dx : -m.dx;
-        cell = i_old;
-    } else if (i_old < i_new) {
-        lo = r_old; up = 1.0; sgn = m.dx; cell = i_old;
-    } else {
-        lo = r_new; up = 1.0; sgn = -m.dx; cell = i_new;
-    }
-    vi = update_jv<D, LP, WITH_B>(acc, bfield, lo, up, cell, w, qm, sgn, scaling, vi, m);
-    if (i_old != i_new) {
-        if (i_old < i_new) {
-            vi = update_jv<D, LP, WITH_B>(acc, bfield, 0.0, r_new, i_new, w, qm, m.dx, scaling, vi, m);
-            for (int c = i_old + 1; c <= i_new - 1; ++c)
-                vi = update_jv<D, LP, WITH_B>(acc, bfield, 0.0, 1.0, c, w, qm, m.dx, scaling, vi, m);
-        } else {
-            vi = update_jv<D, LP, WITH_B>(acc, bfield, 0.0, r_old, i_old, w, qm, -m.dx, scaling, vi, m);
-            for (int c = i_new + 1; c <= i_old - 1; ++c)
-                vi = update_jv<D, LP, WITH_B>(acc, bfield, 0.0, 1.0, c, w, qm, -m.dx, scaling, vi, m);
+    if (!same) {
+        const int g_new = first_dof<D>(pn, m);
+#pragma unroll
+        for (int k = 0; k <= D; ++k) {
+            const double s = fwd ? B[k] : B[k] - prim_full<D>(k);
+            acc.add(slot_base + g_new + k, ws_dx * s);
+            if (WITH_B) bsum = fma(s, bfield[g_new + k], bsum);
+        }
+        // whole cells strictly between (rare: |dt v| > dx)
+        const int lo = fwd ? po.c : pn.c, hi = fwd ? pn.c : po.c;
+        for (int c = lo + 1; c < hi; ++c) {
+            const int g = wrap_index(c - D, m);
+#pragma unroll
+            for (int k = 0; k <= D; ++k) {
+                const double s = fwd ? prim_full<D>(k) : -prim_full<D>(k);
+                acc.add(slot_base + g + k, ws_dx * s);
+                if (WITH_B) bsum = fma(s, bfield[g + k], bsum);
+            }
         }
     }
+    if (WITH_B) vi = fma(-qm_dx, bsum, vi);
     return vi;
+}
+
+// ---- building blocks shared by the per-operator and the fused passes --------------------
+// operatorHE kick at a located particle (hamiltonian_splitting_1d2v.jl:198-215)
+template <int D0, int D1>
+__device__ __forceinline__ void kick_e(Particle &p, int g0, int g1, const double (&b0)[D0 + 1], const double (&b1)[D1 + 1],
+                                       const double *se1, const double *se2, double dtqm)
+{
+    p.v1 = fma(dtqm, gather_h<D1>(se1, g1, b1), p.v1);
+    p.v2 = fma(dtqm, gather_h<D0>(se2, g0, b0), p.v2);
+}
+// operatorHp2 at a located particle (:141-167): v1 += dt q/m v2 B(x); j2 += w v2 N(x)
+template <int D0, int D1, bool LP>
+__device__ __forceinline__ void push_p2(Particle &p, int g0, int g1, const double (&b0)[D0 + 1], const double (&b1)[D1 + 1],
+                                        const double *sb, double dtqm, double ws0, const Acc<LP> &acc, int slot_base)
+{
+    const double bf = gather_h<D1>(sb, g1, b1);
+    p.v1 = fma(dtqm * p.v2, bf, p.v1);
+    deposit_h<D0, LP>(acc, slot_base + g0, b0, ws0 * p.v2);
+}
+// first dof of the degree-(D0) and degree-(D1) stencils of one position (D1 in {D0-1, D0})
+template <int D0, int D1>
+__device__ __forceinline__ void first_dofs(const Pos &ps, const Mesh1D &m, int &g0, int &g1)
+{
+    g0 = first_dof<D0>(ps, m);
+    g1 = (D1 == D0) ? g0 : wrap_next(g0 + (D0 - D1), m.n);
 }
 
 // ---- operatorHE{1,2}  (hamiltonian_splitting_1d2v.jl:198-215), also Boris push_v_epart!
@@ -90,22 +129,20 @@ __device__ __forceinline__ double add_current_update_v(const Acc<LP> &acc, const
 template <int D0, int D1>
 struct OpHE {
     static constexpr int READ = ROW_X | ROW_V1 | ROW_V2, WRITE = ROW_V1 | ROW_V2;
-    static constexpr int NF = 2;
+    static constexpr int NF = 2, NG = 0, NS = 0;
     static constexpr bool DEPOSIT = false;
     struct Params { double dtqm; };
     template <bool LP>
     static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpHE> &P, const double *sf, const Acc<LP> &)
     {
-        int c;
-        double t;
-        cell_offset(p.x, P.m, c, t);
+        const int nh = P.m.n + kHalo;
+        const Pos ps = locate(p.x, P.m);
+        int g0, g1;
+        first_dofs<D0, D1>(ps, P.m, g0, g1);
         double b1[D1 + 1], b0[D0 + 1];
-        bspline_basis<D1>(t, b1);
-        bspline_basis<D0>(t, b0);
-        const double e1 = gather<D1>(sf, c, b1, P.m);
-        const double e2 = gather<D0>(sf + P.m.n, c, b0, P.m);
-        p.v1 = p.v1 + P.op.dtqm * e1;
-        p.v2 = p.v2 + P.op.dtqm * e2;
+        basis_pp<D1>(ps.t, b1);
+        basis_pp<D0>(ps.t, b0);
+        kick_e<D0, D1>(p, g0, g1, b0, b1, sf, sf + nh, P.op.dtqm);
     }
 };
 
@@ -113,52 +150,90 @@ struct OpHE {
 template <int D0, int D1>
 struct OpHp2 {
     static constexpr int READ = ROW_X | ROW_V1 | ROW_V2 | ROW_W, WRITE = ROW_V1;
-    static constexpr int NF = 1;
+    static constexpr int NF = 1, NG = 1, NS = 0;
     static constexpr bool DEPOSIT = true;
-    struct Params { double dtqm, charge, cw, scaling0; };
+    struct Params { double dtqm, wscale0; };   // wscale0 = charge * common_weight * scaling_0
     template <bool LP>
     static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpHp2> &P, const double *sf, const Acc<LP> &acc)
     {
-        int c;
-        double t;
-        cell_offset(p.x, P.m, c, t);
+        const Pos ps = locate(p.x, P.m);
+        int g0, g1;
+        first_dofs<D0, D1>(ps, P.m, g0, g1);
         double b1[D1 + 1], b0[D0 + 1];
-        bspline_basis<D1>(t, b1);
-        bspline_basis<D0>(t, b0);
-        const double b = gather<D1>(sf, c, b1, P.m);
-        p.v1 = p.v1 + P.op.dtqm * p.v2 * b;
-        double w = p.w * P.op.charge;
-        w = w * P.op.cw;
-        w = w * p.v2;
-        deposit<D0, LP>(acc, 0, c, b0, w, P.op.scaling0, P.m);
+        basis_pp<D1>(ps.t, b1);
+        basis_pp<D0>(ps.t, b0);
+        push_p2<D0, D1, LP>(p, g0, g1, b0, b1, sf, P.op.dtqm, p.w * P.op.wscale0, acc, 0);
     }
 };
 
 // ---- operatorHp1{1,2}  (hamiltonian_splitting_1d2v.jl:48-106).  fields: [b];
-//      deposit j1 (D1) at acc[0..n) and, when RHO, rho (D0) at acc[n..2n).
+//      deposit j1 (D1) into grid 0 and, when RHO, rho (D0) into grid 1.
 //      RHO=false is used inside strang_splitting!, where that rho is dead data.
 template <int D0, int D1, bool RHO>
 struct OpHp1 {
     static constexpr int READ = ROW_X | ROW_V1 | ROW_V2 | ROW_W, WRITE = ROW_X | ROW_V2;
-    static constexpr int NF = 1;
+    static constexpr int NF = 1, NG = RHO ? 2 : 1, NS = 0;
     static constexpr bool DEPOSIT = true;
-    struct Params { double dt, qm, charge, cw, scaling0, scaling1; };
+    struct Params { double dt, qm_dx, wscale0, wscale1_dx; };   // wscale1_dx = charge*cw*scaling_1*dx
     template <bool LP>
     static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpHp1> &P, const double *sf, const Acc<LP> &acc)
     {
-        const double x_new = p.x + P.op.dt * p.v1;
-        double wi = p.w * P.op.charge;
-        wi = wi * P.op.cw;
-        p.v2 = add_current_update_v<D1, LP, true, false>(acc, sf, p.x, x_new, wi, P.op.qm, P.op.scaling1, p.v2, P.m);
+        const double x_new = fma(P.op.dt, p.v1, p.x);
+        const Pos po = locate(p.x, P.m);
+        Pos pn = locate(x_new, P.m);
+        p.v2 = current_update_v<D1, LP, true>(acc, 0, sf, po, pn, p.w * P.op.wscale1_dx, P.op.qm_dx, p.v2, P.m);
         p.x = mod_julia(x_new, P.m.Lx);
         if (RHO) {
-            int c;
-            double t;
-            cell_offset(p.x, P.m, c, t);
+            if (p.x != x_new) pn = locate(p.x, P.m);
             double b0[D0 + 1];
-            bspline_basis<D0>(t, b0);
-            deposit<D0, LP>(acc, P.m.n, c, b0, wi, P.op.scaling0, P.m);
+            basis_pp<D0>(pn.t, b0);
+            deposit_h<D0, LP>(acc, (P.m.n + kHalo) + first_dof<D0>(pn, P.m), b0, p.w * P.op.wscale0);
         }
+    }
+};
+
+// ---- fused [HE x NHE, Hp2, Hp1, Hp2] of one Strang step (hamiltonian_splitting.jl:98-108).
+// Inside strang_splitting! the operators HE(dt/2), Hp2(dt/2), Hp1(dt), Hp2(dt/2) only exchange
+// data through the particles: the HE kick reads e1, e2, the three pushes read b (which
+// compute_b_from_e! updated from the *old* e2 before the pass), and their deposits j2, j1, j2
+// feed field solves whose results are first read by the trailing HE.  One pass therefore
+// performs all four: 32 B read + 24 B written per particle instead of 4 passes (168 B).
+// NHE = 2 additionally folds in the trailing HE of the previous step (fields e1T, e2T), which
+// is separated from this step's leading HE only by field-only updates.
+//   fields: [e1, e2] x NHE, b      grids: j2 (first Hp2), j1, j2 (second Hp2)
+template <int D0, int D1, int NHE>
+struct OpStrangFused {
+    static constexpr int READ = ROW_X | ROW_V1 | ROW_V2 | ROW_W, WRITE = ROW_X | ROW_V1 | ROW_V2;
+    static constexpr int NF = 2 * NHE + 1, NG = 3, NS = 0;
+    static constexpr bool DEPOSIT = true;
+    struct Params { double dtqm_e[2], dtqm_p2, dt, qm_dx, wscale0, wscale1_dx; };
+    template <bool LP>
+    static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpStrangFused> &P, const double *sf,
+                                                 const Acc<LP> &acc)
+    {
+        const int nh = P.m.n + kHalo;
+        const double *sb = sf + 2 * NHE * nh;
+        Pos ps = locate(p.x, P.m);
+        int g0, g1;
+        first_dofs<D0, D1>(ps, P.m, g0, g1);
+        double b1[D1 + 1], b0[D0 + 1];
+        basis_pp<D1>(ps.t, b1);
+        basis_pp<D0>(ps.t, b0);
+#pragma unroll
+        for (int h = 0; h < NHE; ++h) kick_e<D0, D1>(p, g0, g1, b0, b1, sf + 2 * h * nh, sf + (2 * h + 1) * nh, P.op.dtqm_e[h]);
+        const double ws0 = p.w * P.op.wscale0;
+        push_p2<D0, D1, LP>(p, g0, g1, b0, b1, sb, P.op.dtqm_p2, ws0, acc, 0);
+        // Hp1
+        const double x_new = fma(P.op.dt, p.v1, p.x);
+        Pos pn = locate(x_new, P.m);
+        p.v2 = current_update_v<D1, LP, true>(acc, nh, sb, ps, pn, p.w * P.op.wscale1_dx, P.op.qm_dx, p.v2, P.m);
+        p.x = mod_julia(x_new, P.m.Lx);
+        if (p.x != x_new) pn = locate(p.x, P.m);
+        // second Hp2 at the new position
+        first_dofs<D0, D1>(pn, P.m, g0, g1);
+        basis_pp<D1>(pn.t, b1);
+        basis_pp<D0>(pn.t, b0);
+        push_p2<D0, D1, LP>(p, g0, g1, b0, b1, sb, P.op.dtqm_p2, ws0, acc, 2 * nh);
     }
 };
 
@@ -166,40 +241,40 @@ struct OpHp1 {
 template <int D1>
 struct OpHB11 {
     static constexpr int READ = ROW_X | ROW_V1, WRITE = ROW_V1;
-    static constexpr int NF = 1;
+    static constexpr int NF = 1, NG = 0, NS = 0;
     static constexpr bool DEPOSIT = false;
     struct Params { double dt; };
     template <bool LP>
     static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpHB11> &P, const double *sf, const Acc<LP> &)
     {
-        int c;
-        double t;
-        cell_offset(p.x, P.m, c, t);
+        const Pos ps = locate(p.x, P.m);
         double b1[D1 + 1];
-        bspline_basis<D1>(t, b1);
-        p.v1 = p.v1 + P.op.dt * gather<D1>(sf, c, b1, P.m);
+        basis_pp<D1>(ps.t, b1);
+        p.v1 = fma(P.op.dt, gather_h<D1>(sf, first_dof<D1>(ps, P.m), b1), p.v1);
     }
 };
 
-// ---- 1d1v operatorHp1 (hamiltonian_splitting_1d1v.jl:70-94): j1 only, v unchanged
+// ---- 1d1v operatorHp1 (hamiltonian_splitting_1d1v.jl:70-94): j1 only, v unchanged;
+//      new index by floor (pmc1d.jl:487)
 template <int D1>
 struct OpHp111 {
     static constexpr int READ = ROW_X | ROW_V1 | ROW_W, WRITE = ROW_X;
-    static constexpr int NF = 0;
+    static constexpr int NF = 0, NG = 1, NS = 0;
     static constexpr bool DEPOSIT = true;
-    struct Params { double dt, charge, cw, scaling1; };
+    struct Params { double dt, wscale1_dx; };
     template <bool LP>
     static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpHp111> &P, const double *, const Acc<LP> &acc)
     {
-        const double x_new = p.x + P.op.dt * p.v1;
-        const double wi = P.op.charge * p.w * P.op.cw;  // get_charge (particle_group.jl:67-69)
-        add_current_update_v<D1, LP, false, true>(acc, nullptr, p.x, x_new, wi, 0.0, P.op.scaling1, p.v1, P.m);
+        const double x_new = fma(P.op.dt, p.v1, p.x);
+        const Pos po = locate(p.x, P.m);
+        Pos pn;
+        cell_offset_floor(x_new, P.m, pn.c, pn.t);
+        current_update_v<D1, LP, false>(acc, 0, nullptr, po, pn, p.w * P.op.wscale1_dx, 0.0, 0.0, P.m);
         p.x = mod_julia(x_new, P.m.Lx);
     }
 };
 
 // ---- Boris push_v_bpart! (hamiltonian_splitting_boris.jl:211-233). fields: [b_mid]
-template <int D1>
 __device__ __forceinline__ void boris_rotate(Particle &p, double bfield, double qmdt)
 {
     bfield = qmdt * bfield;
@@ -214,49 +289,46 @@ __device__ __forceinline__ void boris_rotate(Particle &p, double bfield, double 
 template <int D1>
 struct OpBorisB {
     static constexpr int READ = ROW_X | ROW_V1 | ROW_V2, WRITE = ROW_V1 | ROW_V2;
-    static constexpr int NF = 1;
+    static constexpr int NF = 1, NG = 0, NS = 0;
     static constexpr bool DEPOSIT = false;
     struct Params { double qmdt; };
     template <bool LP>
     static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpBorisB> &P, const double *sf, const Acc<LP> &)
     {
-        int c;
-        double t;
-        cell_offset(p.x, P.m, c, t);
+        const Pos ps = locate(p.x, P.m);
         double b1[D1 + 1];
-        bspline_basis<D1>(t, b1);
-        boris_rotate<D1>(p, gather<D1>(sf, c, b1, P.m), P.op.qmdt);
+        basis_pp<D1>(ps.t, b1);
+        boris_rotate(p, gather_h<D1>(sf, first_dof<D1>(ps, P.m), b1), P.op.qmdt);
     }
 };
 
 // ---- Boris push_x_accumulate_j! (hamiltonian_splitting_boris.jl:250-288):
-//      deposits w*v1 (D1) -> acc[0..n) and w*v2 (D0) -> acc[n..2n) at the un-wrapped midpoint
+//      deposits w*v1 (D1) -> grid 0 and w*v2 (D0) -> grid 1 at the un-wrapped midpoint
 template <int D0, int D1, bool LP>
-__device__ __forceinline__ void boris_push_x(Particle &p, double dt, double charge, double cw, double scaling0,
-                                             double scaling1, const Acc<LP> &acc, const Mesh1D &m)
+__device__ __forceinline__ void boris_push_x(Particle &p, double dt, double wscale0, double wscale1, const Acc<LP> &acc,
+                                             const Mesh1D &m)
 {
-    const double x_new = p.x + dt * p.v1;
-    const double wi = charge * p.w * cw;
-    int c;
-    double t;
-    cell_offset((p.x + x_new) * 0.5, m, c, t);
+    const double x_new = fma(dt, p.v1, p.x);
+    const Pos pm = locate((p.x + x_new) * 0.5, m);
+    int g0, g1;
+    first_dofs<D0, D1>(pm, m, g0, g1);
     double b1[D1 + 1], b0[D0 + 1];
-    bspline_basis<D1>(t, b1);
-    bspline_basis<D0>(t, b0);
-    deposit<D1, LP>(acc, 0, c, b1, wi * p.v1, scaling1, m);
-    deposit<D0, LP>(acc, m.n, c, b0, wi * p.v2, scaling0, m);
+    basis_pp<D1>(pm.t, b1);
+    basis_pp<D0>(pm.t, b0);
+    deposit_h<D1, LP>(acc, g1, b1, (p.w * wscale1) * p.v1);
+    deposit_h<D0, LP>(acc, (m.n + kHalo) + g0, b0, (p.w * wscale0) * p.v2);
     p.x = mod_julia(x_new, m.Lx);
 }
 template <int D0, int D1>
 struct OpBorisX {
     static constexpr int READ = ROW_X | ROW_V1 | ROW_V2 | ROW_W, WRITE = ROW_X;
-    static constexpr int NF = 0;
+    static constexpr int NF = 0, NG = 2, NS = 0;
     static constexpr bool DEPOSIT = true;
-    struct Params { double dt, charge, cw, scaling0, scaling1; };
+    struct Params { double dt, wscale0, wscale1; };
     template <bool LP>
     static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpBorisX> &P, const double *, const Acc<LP> &acc)
     {
-        boris_push_x<D0, D1, LP>(p, P.op.dt, P.op.charge, P.op.cw, P.op.scaling0, P.op.scaling1, acc, P.m);
+        boris_push_x<D0, D1, LP>(p, P.op.dt, P.op.wscale0, P.op.wscale1, acc, P.m);
     }
 };
 
@@ -267,27 +339,28 @@ struct OpBorisX {
 template <int D0, int D1>
 struct OpBorisStep {
     static constexpr int READ = ROW_X | ROW_V1 | ROW_V2 | ROW_W, WRITE = ROW_X | ROW_V1 | ROW_V2;
-    static constexpr int NF = 3;
+    static constexpr int NF = 3, NG = 2, NS = 0;
     static constexpr bool DEPOSIT = true;
-    struct Params { double dt, half_dtqm, qmdt, charge, cw, scaling0, scaling1; };
+    struct Params { double dt, half_dtqm, qmdt, wscale0, wscale1; };
     template <bool LP>
     static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpBorisStep> &P, const double *sf, const Acc<LP> &acc)
     {
-        int c;
-        double t;
-        cell_offset(p.x, P.m, c, t);
+        const int nh = P.m.n + kHalo;
+        const Pos ps = locate(p.x, P.m);
+        int g0, g1;
+        first_dofs<D0, D1>(ps, P.m, g0, g1);
         double b1[D1 + 1], b0[D0 + 1];
-        bspline_basis<D1>(t, b1);
-        bspline_basis<D0>(t, b0);
-        const double e1 = gather<D1>(sf, c, b1, P.m);
-        const double e2 = gather<D0>(sf + P.m.n, c, b0, P.m);
-        const double bf = gather<D1>(sf + 2 * P.m.n, c, b1, P.m);
-        p.v1 = p.v1 + P.op.half_dtqm * e1;
-        p.v2 = p.v2 + P.op.half_dtqm * e2;
-        boris_rotate<D1>(p, bf, P.op.qmdt);
-        p.v1 = p.v1 + P.op.half_dtqm * e1;
-        p.v2 = p.v2 + P.op.half_dtqm * e2;
-        boris_push_x<D0, D1, LP>(p, P.op.dt, P.op.charge, P.op.cw, P.op.scaling0, P.op.scaling1, acc, P.m);
+        basis_pp<D1>(ps.t, b1);
+        basis_pp<D0>(ps.t, b0);
+        const double e1 = gather_h<D1>(sf, g1, b1);
+        const double e2 = gather_h<D0>(sf + nh, g0, b0);
+        const double bf = gather_h<D1>(sf + 2 * nh, g1, b1);
+        p.v1 = fma(P.op.half_dtqm, e1, p.v1);
+        p.v2 = fma(P.op.half_dtqm, e2, p.v2);
+        boris_rotate(p, bf, P.op.qmdt);
+        p.v1 = fma(P.op.half_dtqm, e1, p.v1);
+        p.v2 = fma(P.op.half_dtqm, e2, p.v2);
+        boris_push_x<D0, D1, LP>(p, P.op.dt, P.op.wscale0, P.op.wscale1, acc, P.m);
     }
 };
 
@@ -295,51 +368,48 @@ struct OpBorisStep {
 template <int D>
 struct OpCharge {
     static constexpr int READ = ROW_X | ROW_W, WRITE = 0;
-    static constexpr int NF = 0;
+    static constexpr int NF = 0, NG = 1, NS = 0;
     static constexpr bool DEPOSIT = true;
-    struct Params { double charge, cw, scaling; };
+    struct Params { double wscale; };   // charge * common_weight * scaling
     template <bool LP>
     static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpCharge> &P, const double *, const Acc<LP> &acc)
     {
-        int c;
-        double t;
-        cell_offset(p.x, P.m, c, t);
+        const Pos ps = locate(p.x, P.m);
         double b[D + 1];
-        bspline_basis<D>(t, b);
-        deposit<D, LP>(acc, 0, c, b, P.op.charge * p.w * P.op.cw, P.op.scaling, P.m);
+        basis_pp<D>(ps.t, b);
+        deposit_h<D, LP>(acc, first_dof<D>(ps, P.m), b, p.w * P.op.wscale);
     }
 };
 
-// ---- write_step! particle sums (diagnostics.jl:45-92,197-211): acc = [KE, P1, P2, transfer, vvb]
+// ---- write_step! particle sums (diagnostics.jl:45-92,197-211): scalars [KE, P1, P2, transfer, vvb]
 //      fields: [e1, e2, b]
 template <int D0, int D1>
 struct OpDiag {
     static constexpr int READ = ROW_X | ROW_V1 | ROW_V2 | ROW_W, WRITE = 0;
-    static constexpr int NF = 3;
+    static constexpr int NF = 3, NG = 0, NS = 5;
     static constexpr bool DEPOSIT = true;
     struct Params { double charge, mass, cw; };
     template <bool LP>
     static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpDiag> &P, const double *sf, const Acc<LP> &acc)
     {
+        const int nh = P.m.n + kHalo;
         double wm = p.w * P.op.mass;
         wm *= P.op.cw;
         acc.add(0, (p.v1 * p.v1 + p.v2 * p.v2) * wm);
         acc.add(1, p.v1 * wm);
         acc.add(2, p.v2 * wm);
-        int c;
-        double t;
-        cell_offset(p.x, P.m, c, t);
+        const Pos ps = locate(p.x, P.m);
+        int g0, g1;
+        first_dofs<D0, D1>(ps, P.m, g0, g1);
         double b1[D1 + 1], b0[D0 + 1];
-        bspline_basis<D1>(t, b1);
-        bspline_basis<D0>(t, b0);
-        const double e1 = gather<D1>(sf, c, b1, P.m);
-        const double e2 = gather<D0>(sf + P.m.n, c, b0, P.m);
-        const double bf = gather<D1>(sf + 2 * P.m.n, c, b1, P.m);
+        basis_pp<D1>(ps.t, b1);
+        basis_pp<D0>(ps.t, b0);
+        const double e1 = gather_h<D1>(sf, g1, b1);
+        const double e2 = gather_h<D0>(sf + nh, g0, b0);
+        const double bf = gather_h<D1>(sf + 2 * nh, g1, b1);
         const double wq = P.op.charge * p.w * P.op.cw;  // get_charge
         acc.add(3, (p.v1 * e1 + p.v2 * e2) * wq);
-        double wv = p.w * P.op.charge;
-        wv *= P.op.cw;
-        acc.add(4, wv * p.v1 * p.v2 * bf);
+        acc.add(4, wq * p.v1 * p.v2 * bf);
     }
 };
 

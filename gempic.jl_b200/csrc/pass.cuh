@@ -7,11 +7,18 @@
 // A tiny second kernel (reduce_partials) sums the per-block partials in a fixed order, so
 // the deposit is run-to-run deterministic in LANE mode.
 //
+// Shared-memory layout
+//   fields        Op::NF vectors of n + kHalo doubles; the first kHalo dofs are repeated
+//                 after the last one so that a gather reads dofs g0 .. g0+D with ONE
+//                 periodic wrap per particle instead of one per dof.
+//   accumulators  Op::NG grids of n + kHalo slots (same halo trick; the halo is folded back
+//                 when the block reduces) followed by Op::NS scalar slots.
+//
 // Deposit accumulators (SURVEY section 7 "hard parts": fp64 shared atomics are CAS loops):
 //   LANE mode  every lane of every warp owns a private copy of the (tiny) periodic grid:
-//              slot(g) = warp_base[g*32 + lane]. Plain LDS/DADD/STS, no atomics, and bank
+//              slot(s) = warp_base[s*32 + lane]. Plain LDS/DADD/STS, no atomics, and bank
 //              conflict free for any cell pattern (a half-warp's 16 lanes x 8 B always
-//              cover the 32 banks once).  Used when 32*8*n_dofs bytes per warp fit.
+//              cover the 32 banks once).  Used when the copies fit in shared memory.
 //   ATOM mode  `copies` block-shared copies, warp w adds into copy w % copies with
 //              atomicAdd(double) on shared memory. Fallback for larger grids.
 #pragma once
@@ -22,6 +29,8 @@ namespace gempic {
 
 constexpr int kBlock = 128;  // threads per block (4 warps)
 constexpr int kWarps = kBlock / 32;
+constexpr int kHalo = kMaxDegree;
+constexpr int kMaxFields = 5;
 
 enum RowBits : int { ROW_X = 1, ROW_V1 = 2, ROW_V2 = 4, ROW_W = 8 };
 
@@ -39,10 +48,10 @@ struct Particle {
 template <bool LP>
 struct Acc {
     double *p;  // LP: warp base + lane ; ATOM: base of this warp's copy
-    __device__ __forceinline__ void add(int g, double v) const
+    __device__ __forceinline__ void add(int s, double v) const
     {
-        if (LP) p[g * 32] += v;
-        else atomicAdd(p + g, v);
+        if (LP) p[s * 32] += v;
+        else atomicAdd(p + s, v);
     }
 };
 
@@ -51,12 +60,17 @@ struct PassParams {
     Rows r;
     int64_t n_particles;
     Mesh1D m;
-    const double *fields[4];  // Op::NF device field vectors of m.n doubles staged in smem
-    double *partials;         // [gridDim.x][n_acc] (deposit ops only)
-    int n_acc;                // number of accumulator dofs (Op::NG * m.n, or a scalar count)
-    int copies;               // ATOM mode: accumulator copies per block
+    const double *fields[kMaxFields];  // Op::NF device field vectors of m.n doubles staged in smem
+    double *partials;                  // [gridDim.x][Op::NG * m.n + Op::NS] (deposit ops only)
+    int copies;                        // ATOM mode: accumulator copies per block
     typename Op::Params op;
 };
+
+// slots of one accumulator copy / doubles of one reduced output vector
+template <class Op>
+__host__ __device__ constexpr int acc_slots(int n) { return Op::NG * (n + kHalo) + Op::NS; }
+template <class Op>
+__host__ __device__ constexpr int acc_outputs(int n) { return Op::NG * n + Op::NS; }
 
 template <class Op>
 __device__ __forceinline__ void load_pair(const Rows &r, int64_t pair, Particle &a, Particle &b)
@@ -95,22 +109,23 @@ __global__ void __launch_bounds__(kBlock) k_pass(const __grid_constant__ PassPar
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
     const int n = P.m.n;
-    // ---- stage the field dofs this op gathers from --------------------------------------
+    const int nh = n + kHalo;
+    // ---- stage the field dofs this op gathers from (with periodic halo) -------------------
     double *sfield = smem;
 #pragma unroll
     for (int f = 0; f < Op::NF; ++f)
-        for (int i = tid; i < n; i += kBlock) sfield[f * n + i] = P.fields[f][i];
+        for (int i = tid; i < nh; i += kBlock) sfield[f * nh + i] = P.fields[f][i < n ? i : i - n];
     // ---- zero the block-private accumulators --------------------------------------------
-    double *sacc = smem + Op::NF * n;
-    const int n_acc = P.n_acc;
-    const int acc_words = Op::DEPOSIT ? (LP ? n_acc * 32 * kWarps : n_acc * P.copies) : 0;
+    double *sacc = smem + Op::NF * nh;
+    const int slots = acc_slots<Op>(n);
+    const int acc_words = Op::DEPOSIT ? (LP ? slots * 32 * kWarps : slots * P.copies) : 0;
     for (int i = tid; i < acc_words; i += kBlock) sacc[i] = 0.0;
     __syncthreads();
 
     Acc<LP> acc;
     {
         const int warp = tid >> 5, lane = tid & 31;
-        acc.p = LP ? sacc + (size_t)warp * n_acc * 32 + lane : sacc + (size_t)(warp % (P.copies > 0 ? P.copies : 1)) * n_acc;
+        acc.p = LP ? sacc + (size_t)warp * slots * 32 + lane : sacc + (size_t)(warp % (P.copies > 0 ? P.copies : 1)) * slots;
     }
 
     // ---- stream the particles: pairs, two batches in flight -----------------------------
@@ -145,19 +160,35 @@ __global__ void __launch_bounds__(kBlock) k_pass(const __grid_constant__ PassPar
     // ---- hierarchical reduce: lanes -> warps -> one partial vector per block ------------
     if (Op::DEPOSIT) {
         __syncthreads();
-        double *out = P.partials + (size_t)blockIdx.x * n_acc;
-        for (int g = tid; g < n_acc; g += kBlock) {
+        const int n_out = acc_outputs<Op>(n);
+        double *out = P.partials + (size_t)blockIdx.x * n_out;
+        for (int o = tid; o < n_out; o += kBlock) {
+            // output o -> first slot s0 (+ its halo image s1, or -1)
+            int s0, s1 = -1;
+            if (o < Op::NG * n) {
+                const int k = o / n, g = o - k * n;
+                s0 = k * nh + g;
+                if (g < kHalo) s1 = s0 + n;
+            } else {
+                s0 = Op::NG * nh + (o - Op::NG * n);
+            }
             double s = 0.0;
             if (LP) {
                 for (int w = 0; w < kWarps; ++w) {
-                    const double *base = sacc + (size_t)w * n_acc * 32 + (size_t)g * 32;
+                    const double *base = sacc + (size_t)w * slots * 32;
 #pragma unroll 8
-                    for (int l = 0; l < 32; ++l) s += base[(l + g) & 31];  // rotated: conflict free
+                    for (int l = 0; l < 32; ++l) s += base[(size_t)s0 * 32 + ((l + o) & 31)];  // rotated: conflict free
+                    if (s1 >= 0)
+#pragma unroll 8
+                        for (int l = 0; l < 32; ++l) s += base[(size_t)s1 * 32 + ((l + o) & 31)];
                 }
             } else {
-                for (int c = 0; c < P.copies; ++c) s += sacc[(size_t)c * n_acc + g];
+                for (int c = 0; c < P.copies; ++c) {
+                    s += sacc[(size_t)c * slots + s0];
+                    if (s1 >= 0) s += sacc[(size_t)c * slots + s1];
+                }
             }
-            out[g] = s;
+            out[o] = s;
         }
     }
 }
@@ -165,13 +196,5 @@ __global__ void __launch_bounds__(kBlock) k_pass(const __grid_constant__ PassPar
 // out[g] = sum_b partials[b][g], b ascending; one warp per dof, fixed tree -> deterministic.
 __global__ void k_reduce_partials(const double *__restrict__ partials, int n_blocks, int n_acc,
                                   double *__restrict__ out);
-
-// host-side launch plan of a pass
-struct PassPlan {
-    bool lane_private;
-    int copies;
-    int grid;
-    size_t smem_bytes;
-};
 
 }  // namespace gempic

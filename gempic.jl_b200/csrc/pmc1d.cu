@@ -9,18 +9,16 @@ namespace gempic {
 template <int D>
 struct OpEval {
     static constexpr int READ = ROW_X, WRITE = ROW_V1;
-    static constexpr int NF = 1;
+    static constexpr int NF = 1, NG = 0, NS = 0;
     static constexpr bool DEPOSIT = false;
     struct Params { int unused; };
     template <bool LP>
     static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpEval> &P, const double *sf, const Acc<LP> &)
     {
-        int c;
-        double t;
-        cell_offset(p.x, P.m, c, t);
+        const Pos ps = locate(p.x, P.m);
         double b[D + 1];
-        bspline_basis<D>(t, b);
-        p.v1 = gather<D>(sf, c, b, P.m);
+        basis_pp<D>(ps.t, b);
+        p.v1 = gather_h<D>(sf, first_dof<D>(ps, P.m), b);
     }
 };
 
@@ -28,16 +26,21 @@ struct OpEval {
 template <int D, bool WITH_B>
 struct OpCurrent {
     static constexpr int READ = ROW_X | ROW_V1 | ROW_W | (WITH_B ? ROW_V2 : 0), WRITE = WITH_B ? ROW_V2 : 0;
-    static constexpr int NF = WITH_B ? 1 : 0;
+    static constexpr int NF = WITH_B ? 1 : 0, NG = 1, NS = 0;
     static constexpr bool DEPOSIT = true;
-    struct Params { double qm, scaling; };
+    struct Params { double qm_dx, scaling_dx; };
     template <bool LP>
     static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpCurrent> &P, const double *sf, const Acc<LP> &acc)
     {
-        if (WITH_B)
-            p.v2 = add_current_update_v<D, LP, true, false>(acc, sf, p.x, p.v1, p.w, P.op.qm, P.op.scaling, p.v2, P.m);
-        else
-            add_current_update_v<D, LP, false, true>(acc, nullptr, p.x, p.v1, p.w, P.op.qm, P.op.scaling, 0.0, P.m);
+        const Pos po = locate(p.x, P.m);
+        Pos pn;
+        if (WITH_B) {
+            pn = locate(p.v1, P.m);
+            p.v2 = current_update_v<D, LP, true>(acc, 0, sf, po, pn, p.w * P.op.scaling_dx, P.op.qm_dx, p.v2, P.m);
+        } else {
+            cell_offset_floor(p.v1, P.m, pn.c, pn.t);   // 1d1v form: floor for the new index (:487)
+            current_update_v<D, LP, false>(acc, 0, nullptr, po, pn, p.w * P.op.scaling_dx, 0.0, 0.0, P.m);
+        }
     }
 };
 
@@ -50,8 +53,7 @@ void pmc1d_add_charge_dev(Pmc1D &p, const double *x, const double *w, int64_t n,
         P.r.w = const_cast<double *>(w);
         P.n_particles = n;
         P.m = p.mesh(p.Lx);
-        P.n_acc = p.n_grid;
-        P.op = {charge, cw, p.scaling};
+        P.op = {charge * cw * p.scaling};
         launch_pass<Op>(P, &p.scratch, rho_out);
     });
 }
@@ -84,8 +86,7 @@ void pmc1d_add_current_dev(Pmc1D &p, const double *x_old, const double *x_new, c
             P.n_particles = n;
             P.m = p.mesh(p.Lx);
             P.fields[0] = bfield;
-            P.n_acc = p.n_grid;
-            P.op = {qm, p.scaling};
+            P.op = {qm * p.delta_x, p.scaling * p.delta_x};
             launch_pass<Op>(P, &p.scratch, j_out);
         } else {
             using Op = OpCurrent<D, false>;
@@ -95,8 +96,7 @@ void pmc1d_add_current_dev(Pmc1D &p, const double *x_old, const double *x_new, c
             P.r.w = const_cast<double *>(w);
             P.n_particles = n;
             P.m = p.mesh(p.Lx);
-            P.n_acc = p.n_grid;
-            P.op = {qm, p.scaling};
+            P.op = {qm * p.delta_x, p.scaling * p.delta_x};
             launch_pass<Op>(P, &p.scratch, j_out);
         }
     });
@@ -115,7 +115,6 @@ void diag_particle_sums(ParticleGroup &pg, Pmc1D &ks0, Pmc1D &ks1, const Maxwell
         P.fields[0] = e1;
         P.fields[1] = e2;
         P.fields[2] = b;
-        P.n_acc = 5;
         P.op = {pg.charge, pg.mass, pg.common_weight};
         launch_pass<Op>(P, &scratch, out5);
     });

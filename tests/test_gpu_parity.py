@@ -76,6 +76,42 @@ def test_strang_resident_equals_host_path(orc, gp):
         assert np.array_equal(getattr(sa, name), getattr(sb, name))
 
 
+@pytest.mark.parametrize("deg0,deg1", [(3, 2), (3, 3), (2, 1), (1, 0)])
+@pytest.mark.parametrize("steps,resident", [(1, False), (4, True), (4, False)])
+def test_strang_fused_passes(orc, gp, deg0, deg1, steps, resident):
+    """gempic_hs_set_fusion(1): [HE,Hp2,Hp1,Hp2] in one pass and, for number_steps > 1, the trailing HE of
+    a step folded into the next step's pass -- the same trajectory as the reference's operator sequence."""
+    n = 50_001
+    state = weibel_state(n, L_WEIBEL, seed=77 + deg0)
+    state[1] *= 4.0   # ~25 % of the particles cross a cell boundary per step
+    so, sg = both(orc, gp, state, L_WEIBEL, nx=32, deg0=deg0, deg1=deg1)
+    so.init_fields(b_amp=1e-2, e2_amp=1e-3), sg.init_fields(b_amp=1e-2, e2_amp=1e-3)
+    ho, hg = so.splitting(), sg.splitting(resident=resident)
+    hg.set_fusion(True)
+    ho.strang_splitting(0.05, steps)
+    hg.strang_splitting(0.05, steps)
+    if resident:
+        hg.sync_fields()
+    assert particle_err(sg.particles(), so.particles(), L_WEIBEL) < 1e-11
+    check_fields(so, sg, tol=1e-11)
+
+
+def test_strang_fused_equals_unfused_long_run(gp):
+    """200 steps, fused (one call) vs one kernel per operator: diagnostics-level agreement."""
+    n = 200_000
+    state = landau_state(n, L_LANDAU, seed=21)
+    sa, sb = Sim1D(gp, state, L_LANDAU).init_fields(), Sim1D(gp, state, L_LANDAU).init_fields()
+    ha, hb = sa.splitting(resident=True), sb.splitting(resident=True)
+    hb.set_fusion(True)
+    ha.strang_splitting(0.05, 200)
+    hb.strang_splitting(0.05, 200)
+    ha.sync_fields(), hb.sync_fields()
+    for name in ("e1", "e2", "b"):
+        assert rel_err(getattr(sb, name), getattr(sa, name)) < 1e-7, name
+    energy = lambda s: float(s.mx.inner_product(s.e1, s.e1, 2))
+    assert abs(energy(sa) - energy(sb)) < 1e-7 * abs(energy(sa))
+
+
 def test_multicell_and_backward_crossings(orc, gp):
     # fast particles: several cells per step in both directions, x_new < 0 (trunc quirk, SURVEY Q1)
     n = 20_000
