@@ -128,20 +128,50 @@ __global__ void __launch_bounds__(kBlock) k_pass(const __grid_constant__ PassPar
         acc.p = LP ? sacc + (size_t)warp * slots * 32 + lane : sacc + (size_t)(warp % (P.copies > 0 ? P.copies : 1)) * slots;
     }
 
-    // ---- stream the particles: pairs, two batches in flight -----------------------------
+    // ---- stream the particles: pairs, two batches per iteration -------------------------
+    // Deposit ops are limited to a few warps per SM by their shared-memory accumulators, so
+    // registers are plentiful: the next iteration's rows are loaded before the current one is
+    // processed (software prefetch), which hides the HBM latency those few warps cannot.
     const int64_t n_pairs = P.n_particles >> 1;
     const int64_t T = (int64_t)gridDim.x * kBlock;
     int64_t p = (int64_t)blockIdx.x * kBlock + tid;
-    for (; p + T < n_pairs; p += 2 * T) {
+    if (Op::DEPOSIT) {
         Particle a0, a1, b0, b1;
-        load_pair<Op>(P.r, p, a0, a1);
-        load_pair<Op>(P.r, p + T, b0, b1);
-        Op::apply(a0, P, sfield, acc);
-        Op::apply(a1, P, sfield, acc);
-        store_pair<Op>(P.r, p, a0, a1);
-        Op::apply(b0, P, sfield, acc);
-        Op::apply(b1, P, sfield, acc);
-        store_pair<Op>(P.r, p + T, b0, b1);
+        bool have = p + T < n_pairs;
+        if (have) {
+            load_pair<Op>(P.r, p, a0, a1);
+            load_pair<Op>(P.r, p + T, b0, b1);
+        }
+        while (have) {
+            const int64_t q = p + 2 * T;
+            const bool have_next = q + T < n_pairs;
+            Particle c0, c1, d0, d1;
+            if (have_next) {
+                load_pair<Op>(P.r, q, c0, c1);
+                load_pair<Op>(P.r, q + T, d0, d1);
+            }
+            Op::apply(a0, P, sfield, acc);
+            Op::apply(a1, P, sfield, acc);
+            store_pair<Op>(P.r, p, a0, a1);
+            Op::apply(b0, P, sfield, acc);
+            Op::apply(b1, P, sfield, acc);
+            store_pair<Op>(P.r, p + T, b0, b1);
+            a0 = c0; a1 = c1; b0 = d0; b1 = d1;
+            p = q;
+            have = have_next;
+        }
+    } else {
+        for (; p + T < n_pairs; p += 2 * T) {
+            Particle a0, a1, b0, b1;
+            load_pair<Op>(P.r, p, a0, a1);
+            load_pair<Op>(P.r, p + T, b0, b1);
+            Op::apply(a0, P, sfield, acc);
+            Op::apply(a1, P, sfield, acc);
+            store_pair<Op>(P.r, p, a0, a1);
+            Op::apply(b0, P, sfield, acc);
+            Op::apply(b1, P, sfield, acc);
+            store_pair<Op>(P.r, p + T, b0, b1);
+        }
     }
     for (; p < n_pairs; p += T) {
         Particle a0, a1;

@@ -109,12 +109,20 @@ struct Mesh1D {
     int pow2;   // n is a power of two -> mask instead of %
 };
 
-// floored modulo into [0, n)
+// floored modulo into [0, n).  Particles sit within one period of the domain, so g is in
+// [-n, 2n) and one conditional add/subtract suffices; anything further out (|dt v| > L)
+// takes the out-of-line integer division.
+static __device__ __noinline__ int wrap_index_far(int g, int n)
+{
+    g %= n;
+    return g < 0 ? g + n : g;
+}
 __device__ __forceinline__ int wrap_index(int g, const Mesh1D &m)
 {
-    if (m.pow2) return g & (m.n - 1);
-    g %= m.n;
-    return g < 0 ? g + m.n : g;
+    const int n = m.n;
+    if (__builtin_expect((unsigned)(g + n) >= (unsigned)(3 * n), 0)) return wrap_index_far(g, n);
+    g = g < 0 ? g + n : g;
+    return g >= n ? g - n : g;
 }
 // g is known to be in [0, 2n): one conditional subtraction
 __device__ __forceinline__ int wrap_next(int g, int n) { return g >= n ? g - n : g; }
