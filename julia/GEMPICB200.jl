@@ -1,0 +1,269 @@
+# GEMPICB200.jl -- Julia binding of libgempic_b200.so (include/gempic_b200.h).
+#
+# Drop-in for the particle-mesh hot path of GEMPIC.jl: the types keep the reference's names,
+# constructor signatures and field names, the functions keep their names and argument order;
+# each method body is one `ccall`.  Host arrays are only borrowed for the duration of a call
+# (`ccall` roots `Ref`/`Array` arguments).  Julia is not available in the build image, so this file
+# is desk-checked against the header; the Python mirror gempic.jl_b200/api.py drives the same
+# entry points under test.
+#
+#   using GEMPICB200   # instead of `using GEMPIC` for the types below
+module GEMPICB200
+
+export OneDGrid, ParticleGroup, ParticleMeshCoupling1D, Maxwell1DFEM,
+       HamiltonianSplitting, HamiltonianSplittingBoris, strang_splitting!, staggering!,
+       operatorHp1, operatorHp2, operatorHE, operatorHB, solve_poisson!,
+       add_charge!, evaluate, add_current_update_v!, compute_e_from_rho!, compute_e_from_j!,
+       compute_e_from_b!, compute_b_from_e!, inner_product, l2norm_squared, l2projection!,
+       compute_rhs_from_function!, write_step!, upload!, download!
+
+const LIB = get(ENV, "GEMPIC_B200_LIB", joinpath(@__DIR__, "..", "gempic.jl_b200", "libgempic_b200.so"))
+const Handle = UInt64
+
+# status -> exception, mirroring the reference: ArgumentError for its `throw(ArgumentError(..))`
+# sites (GEMPIC_EINVAL), AssertionError for its `@assert`s (GEMPIC_EASSERT).
+function check(rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:gempic_last_error, LIB), Cstring, ()))
+    rc == 1 && throw(ArgumentError(msg))
+    rc == 2 && throw(AssertionError(msg))
+    error("gempic_b200 status $rc: $msg")
+end
+
+const _initialised = Ref(false)
+function init(device::Integer = parse(Int, get(ENV, "LOCAL_RANK", "0")))
+    _initialised[] && return
+    check(ccall((:gempic_init, LIB), Cint, (Cint,), device))
+    _initialised[] = true
+    atexit(() -> ccall((:gempic_finalize, LIB), Cint, ()))
+end
+
+# ---- mesh (src/mesh.jl:52-67): only the scalars are read by the hot path --------------------------
+struct OneDGrid
+    xmin::Float64
+    xmax::Float64
+    nx::Int
+    dimx::Float64
+    OneDGrid(xmin, xmax, nx) = new(xmin, xmax, nx, xmax - xmin)
+end
+
+# ---- ParticleGroup{D,V} (src/particle_group.jl:15-46) -------------------------------------------
+# `array` keeps the reference layout (D+V+W) x N.  It is the *host mirror*: `upload!` after filling
+# it (sampling), `download!` before reading it.  `getproperty(pg, :array)` could do this lazily with
+# a dirty flag (as the Python mirror does); kept explicit here so that a 1e9-particle run never
+# copies 32 GB by accident.
+mutable struct ParticleGroup{D,V}
+    dims::Tuple{Int,Int}
+    n_particles::Int
+    array::Array{Float64,2}
+    common_weight::Float64
+    charge::Float64
+    mass::Float64
+    n_weights::Int
+    q_over_m::Float64
+    handle::Handle
+    function ParticleGroup{D,V}(n_particles; charge = 1.0, mass = 1.0, n_weights = 1, common_weight = 0.0,
+                                host_mirror = true) where {D,V}
+        init()
+        common_weight == 0.0 && (common_weight = 1.0 / n_particles)
+        h = Ref{Handle}(0)
+        check(ccall((:gempic_pg_create, LIB), Cint,
+                    (Cint, Cint, Cint, Int64, Cdouble, Cdouble, Cdouble, Ref{Handle}),
+                    D, V, n_weights, n_particles, charge, mass, common_weight, h))
+        array = host_mirror ? zeros(Float64, D + V + n_weights, n_particles) : zeros(Float64, D + V + n_weights, 0)
+        pg = new(( D, V ), n_particles, array, common_weight, charge, mass, n_weights, charge / mass, h[])
+        finalizer(p -> ccall((:gempic_pg_destroy, LIB), Cint, (Handle,), p.handle), pg)
+        return pg
+    end
+end
+upload!(pg::ParticleGroup) = check(ccall((:gempic_pg_upload, LIB), Cint, (Handle, Ptr{Cdouble}), pg.handle, pg.array))
+function download!(pg::ParticleGroup)
+    size(pg.array, 2) == pg.n_particles || (pg.array = zeros(Float64, sum(pg.dims) + pg.n_weights, pg.n_particles))
+    check(ccall((:gempic_pg_download, LIB), Cint, (Handle, Ptr{Cdouble}), pg.handle, pg.array))
+    return pg.array
+end
+get_x(p::ParticleGroup{D,V}, i::Int) where {D,V} = p.array[1:D, i]
+get_v(p::ParticleGroup{D,V}, i::Int) where {D,V} = p.array[(D + 1):(D + V), i]
+get_charge(p::ParticleGroup{D,V}, i::Int; i_wi = 1) where {D,V} = p.charge * p.array[D + V + i_wi, i] * p.common_weight
+get_mass(p::ParticleGroup{D,V}, i::Int; i_wi = 1) where {D,V} = p.mass * p.array[D + V + i_wi, i] * p.common_weight
+sort!(pg::ParticleGroup, pmc) = check(ccall((:gempic_pg_sort, LIB), Cint, (Handle, Handle), pg.handle, pmc.handle))
+
+# ---- ParticleMeshCoupling1D (src/particle_mesh_coupling_1d.jl:26-95) ----------------------------
+mutable struct ParticleMeshCoupling1D
+    dims::Int
+    xmin::Float64
+    Lx::Float64
+    delta_x::Float64
+    n_grid::Int
+    n_dofs::Int
+    no_particles::Int
+    spline_degree::Int
+    n_span::Int
+    scaling::Float64
+    handle::Handle
+    function ParticleMeshCoupling1D(mesh::OneDGrid, no_particles, spline_degree, smoothing_type::Symbol)
+        init()
+        smoothing_type in (:collocation, :galerkin) ||
+            throw(ArgumentError("Smoothing Type $smoothing_type not implemented for kernel_smoother_spline_1d. "))
+        h = Ref{Handle}(0)
+        check(ccall((:gempic_pmc1d_create, LIB), Cint, (Cdouble, Cdouble, Cint, Int64, Cint, Cint, Ref{Handle}),
+                    mesh.xmin, mesh.xmax, mesh.nx, no_particles, spline_degree, smoothing_type == :galerkin ? 1 : 0, h))
+        dx = (mesh.xmax - mesh.xmin) / mesh.nx
+        p = new(1, mesh.xmin, mesh.xmax - mesh.xmin, dx, mesh.nx, mesh.nx, no_particles, spline_degree,
+                spline_degree + 1, smoothing_type == :collocation ? 1 / dx : 1.0, h[])
+        finalizer(q -> ccall((:gempic_pmc1d_destroy, LIB), Cint, (Handle,), q.handle), p)
+        return p
+    end
+end
+
+# batched forms of the per-particle methods (:261-280, :438-453, :296-376, :471-529)
+function add_charge!(rho_dofs::Vector{Float64}, p::ParticleMeshCoupling1D, position::Vector{Float64}, marker_charge::Vector{Float64})
+    check(ccall((:gempic_pmc1d_add_charge, LIB), Cint, (Handle, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cdouble}),
+                p.handle, position, marker_charge, length(position), rho_dofs))
+end
+add_charge!(rho_dofs::Vector{Float64}, p::ParticleMeshCoupling1D, position::Float64, marker_charge::Float64) =
+    add_charge!(rho_dofs, p, [position], [marker_charge])
+add_charge!(rho_dofs::Vector{Float64}, p::ParticleMeshCoupling1D, pg::ParticleGroup) =
+    check(ccall((:gempic_pmc1d_add_charge_pg, LIB), Cint, (Handle, Handle, Ptr{Cdouble}), p.handle, pg.handle, rho_dofs))
+function evaluate(p::ParticleMeshCoupling1D, position::Vector{Float64}, field_dofs::Vector{Float64})
+    out = similar(position)
+    check(ccall((:gempic_pmc1d_evaluate, LIB), Cint, (Handle, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Ptr{Cdouble}),
+                p.handle, position, length(position), field_dofs, out))
+    return out
+end
+evaluate(p::ParticleMeshCoupling1D, position::Float64, field_dofs::Vector{Float64}) = evaluate(p, [position], field_dofs)[1]
+function add_current_update_v!(j_dofs::Vector{Float64}, p::ParticleMeshCoupling1D, position_old::Vector{Float64},
+                               position_new::Vector{Float64}, marker_charge::Vector{Float64}, qoverm::Float64,
+                               bfield_dofs::Vector{Float64}, vi::Vector{Float64})
+    check(ccall((:gempic_pmc1d_add_current_update_v, LIB), Cint,
+                (Handle, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Ptr{Cdouble}),
+                p.handle, position_old, position_new, marker_charge, qoverm, bfield_dofs, vi, length(vi), j_dofs))
+    return vi
+end
+
+# ---- Maxwell1DFEM (src/maxwell_1d_fem.jl:29-177) ------------------------------------------------
+mutable struct Maxwell1DFEM
+    Lx::Float64
+    xmin::Float64
+    delta_x::Float64
+    n_dofs::Int
+    s_deg_0::Int
+    s_deg_1::Int
+    handle::Handle
+    function Maxwell1DFEM(mesh::OneDGrid, degree::Int)
+        init()
+        h = Ref{Handle}(0)
+        check(ccall((:gempic_maxwell1d_create, LIB), Cint, (Cdouble, Cdouble, Cint, Cint, Ref{Handle}),
+                    mesh.xmin, mesh.xmax, mesh.nx, degree, h))
+        m = new(mesh.xmax - mesh.xmin, mesh.xmin, (mesh.xmax - mesh.xmin) / mesh.nx, mesh.nx, degree, degree - 1, h[])
+        finalizer(q -> ccall((:gempic_maxwell1d_destroy, LIB), Cint, (Handle,), q.handle), m)
+        return m
+    end
+end
+compute_e_from_rho!(e::Vector{Float64}, m::Maxwell1DFEM, rho::Vector{Float64}) =
+    check(ccall((:gempic_maxwell1d_compute_e_from_rho, LIB), Cint, (Handle, Ptr{Cdouble}, Ptr{Cdouble}), m.handle, e, rho))
+compute_e_from_j!(e::Vector{Float64}, m::Maxwell1DFEM, j::Vector{Float64}, component::Int) =
+    check(ccall((:gempic_maxwell1d_compute_e_from_j, LIB), Cint, (Handle, Ptr{Cdouble}, Ptr{Cdouble}, Cint), m.handle, e, j, component))
+compute_e_from_b!(e::Vector{Float64}, m::Maxwell1DFEM, dt::Float64, b::Vector{Float64}) =
+    check(ccall((:gempic_maxwell1d_compute_e_from_b, LIB), Cint, (Handle, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}), m.handle, e, dt, b))
+compute_b_from_e!(b::Vector{Float64}, m::Maxwell1DFEM, dt::Float64, e::Vector{Float64}) =
+    check(ccall((:gempic_maxwell1d_compute_b_from_e, LIB), Cint, (Handle, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}), m.handle, b, dt, e))
+function inner_product(m::Maxwell1DFEM, c1::Vector{Float64}, c2::Vector{Float64}, degree)
+    out = Ref{Cdouble}(0)
+    check(ccall((:gempic_maxwell1d_inner_product, LIB), Cint, (Handle, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ref{Cdouble}),
+                m.handle, c1, c2, degree, out))
+    return out[]
+end
+l2norm_squared(m::Maxwell1DFEM, c::Vector{Float64}, degree) = inner_product(m, c, c, degree)
+
+# C callback trampoline for the set-up helpers that take a Julia function of x
+_tramp(x::Cdouble, ctx::Ptr{Cvoid})::Cdouble = unsafe_pointer_to_objref(ctx)[](x)
+function l2projection!(coefs::Vector{Float64}, m::Maxwell1DFEM, f::Function, degree)
+    r = Ref{Function}(f)
+    GC.@preserve r check(ccall((:gempic_maxwell1d_l2projection, LIB), Cint, (Handle, Ptr{Cdouble}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                               m.handle, coefs, @cfunction(_tramp, Cdouble, (Cdouble, Ptr{Cvoid})), pointer_from_objref(r), degree))
+end
+function compute_rhs_from_function!(coefs::Vector{Float64}, m::Maxwell1DFEM, f::Function, degree)
+    r = Ref{Function}(f)
+    GC.@preserve r check(ccall((:gempic_maxwell1d_compute_rhs_from_function, LIB), Cint, (Handle, Ptr{Cdouble}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                               m.handle, coefs, @cfunction(_tramp, Cdouble, (Cdouble, Ptr{Cvoid})), pointer_from_objref(r), degree))
+end
+
+# ---- HamiltonianSplitting{D,V} (src/hamiltonian_splitting.jl:20-86) -----------------------------
+# e_dofs / b_dofs stay the caller's arrays (aliased, :80-81): every call copies them in and the
+# updated values back (3 x n doubles), which is what the reference's tests read after each operator.
+struct HamiltonianSplitting{D,V}
+    dims::Tuple{Int64,Int64}
+    maxwell_solver::Maxwell1DFEM
+    kernel_smoother_0::ParticleMeshCoupling1D
+    kernel_smoother_1::ParticleMeshCoupling1D
+    particle_group::ParticleGroup
+    e_dofs::Array{Array{Float64,1}}
+    b_dofs::Array{Float64,1}
+    j_dofs::Array{Array{Float64,1}}
+    handle::Handle
+    function HamiltonianSplitting{D,V}(maxwell_solver, kernel_smoother_0, kernel_smoother_1, particle_group,
+                                       e_dofs, b_dofs; fuse = true) where {D,V}
+        h = Ref{Handle}(0)
+        check(ccall((:gempic_hs_create, LIB), Cint, (Cint, Cint, Handle, Handle, Handle, Handle, Ref{Handle}),
+                    D, V, maxwell_solver.handle, kernel_smoother_0.handle, kernel_smoother_1.handle, particle_group.handle, h))
+        check(ccall((:gempic_hs_set_fusion, LIB), Cint, (Handle, Cint), h[], fuse ? 1 : 0))
+        j_dofs = [zeros(Float64, kernel_smoother_0.n_dofs) for i in 1:2]
+        return new((D, V), maxwell_solver, kernel_smoother_0, kernel_smoother_1, particle_group, e_dofs, b_dofs, j_dofs, h[])
+    end
+end
+const OP_HP1, OP_HP2, OP_HE, OP_HB = Cint(1), Cint(2), Cint(3), Cint(4)
+_op(h::HamiltonianSplitting, op::Cint, dt::Float64) =
+    check(ccall((:gempic_hs_operator_host, LIB), Cint,
+                (Handle, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                h.handle, op, dt, h.e_dofs[1], h.e_dofs[2], h.b_dofs, h.j_dofs[1], h.j_dofs[2]))
+operatorHp1(h::HamiltonianSplitting, dt::Float64) = _op(h, OP_HP1, dt)   # src/hamiltonian_splitting_1d2v.jl:41-112 / _1d1v.jl:63-98
+operatorHp2(h::HamiltonianSplitting, dt::Float64) = _op(h, OP_HP2, dt)   # :129-176
+operatorHE(h::HamiltonianSplitting, dt::Float64) = _op(h, OP_HE, dt)     # :191-219
+operatorHB(h::HamiltonianSplitting, dt::Float64) = _op(h, OP_HB, dt)     # :234-236 / _1d1v.jl:113-125
+strang_splitting!(h::HamiltonianSplitting, dt::Float64, number_steps::Int) =   # src/hamiltonian_splitting.jl:98-108
+    check(ccall((:gempic_hs_strang_splitting_host, LIB), Cint,
+                (Handle, Cdouble, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                h.handle, dt, number_steps, h.e_dofs[1], h.e_dofs[2], h.b_dofs, h.j_dofs[1], h.j_dofs[2]))
+
+# ---- HamiltonianSplittingBoris (src/hamiltonian_splitting_boris.jl:23-88) -----------------------
+struct HamiltonianSplittingBoris
+    maxwell_solver::Maxwell1DFEM
+    kernel_smoother_0::ParticleMeshCoupling1D
+    kernel_smoother_1::ParticleMeshCoupling1D
+    particle_group::ParticleGroup
+    e_dofs::Array{Array{Float64,1}}
+    b_dofs::Array{Float64,1}
+    handle::Handle
+    function HamiltonianSplittingBoris(maxwell_solver, kernel_smoother_0, kernel_smoother_1, particle_group, e_dofs, b_dofs)
+        h = Ref{Handle}(0)
+        check(ccall((:gempic_boris_create, LIB), Cint, (Handle, Handle, Handle, Handle, Ref{Handle}),
+                    maxwell_solver.handle, kernel_smoother_0.handle, kernel_smoother_1.handle, particle_group.handle, h))
+        return new(maxwell_solver, kernel_smoother_0, kernel_smoother_1, particle_group, e_dofs, b_dofs, h[])
+    end
+end
+staggering!(h::HamiltonianSplittingBoris, dt::Float64) =                     # :99-122
+    check(ccall((:gempic_boris_staggering_host, LIB), Cint, (Handle, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                h.handle, dt, h.e_dofs[1], h.e_dofs[2], h.b_dofs))
+strang_splitting!(h::HamiltonianSplittingBoris, dt::Float64, number_steps::Int) =   # :132-177
+    check(ccall((:gempic_boris_strang_splitting_host, LIB), Cint, (Handle, Cdouble, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                h.handle, dt, number_steps, h.e_dofs[1], h.e_dofs[2], h.b_dofs))
+
+# ---- diagnostics (src/diagnostics.jl) --------------------------------------------------------------
+function solve_poisson!(efield::Vector{Float64}, particle_group::ParticleGroup, kernel_smoother_0::ParticleMeshCoupling1D,
+                        maxwell_solver::Maxwell1DFEM, rho::Vector{Float64})            # :15-31
+    check(ccall((:gempic_solve_poisson, LIB), Cint, (Handle, Handle, Handle, Ptr{Cdouble}, Ptr{Cdouble}),
+                particle_group.handle, kernel_smoother_0.handle, maxwell_solver.handle, efield, rho))
+end
+# one row of TimeHistoryDiagnostics.data (:143-155): the caller push!es it onto its DataFrame
+function write_step!(pg::ParticleGroup, maxwell::Maxwell1DFEM, ks0::ParticleMeshCoupling1D, ks1::ParticleMeshCoupling1D,
+                     time, degree, efield_dofs, bfield_dofs, efield_dofs_n, efield_poisson)   # :186-250
+    out = zeros(Float64, 11)
+    check(ccall((:gempic_diag_write_step, LIB), Cint,
+                (Handle, Handle, Handle, Handle, Cdouble, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                pg.handle, maxwell.handle, ks0.handle, ks1.handle, time, degree, efield_dofs[1], efield_dofs[2], bfield_dofs,
+                efield_dofs_n[1], efield_dofs_n[2], efield_poisson, out))
+    return out
+end
+
+end # module
