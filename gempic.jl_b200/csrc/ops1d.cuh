@@ -201,15 +201,45 @@ struct OpHp1 {
 // NHE = 2 additionally folds in the trailing HE of the previous step (fields e1T, e2T), which
 // is separated from this step's leading HE only by field-only updates.
 //   fields: [e1, e2] x NHE, b      grids: j2 (first Hp2), j1, j2 (second Hp2)
+//
+// Three lane-private grids leave room for only 8 warps per SM, so the pass lives on
+// instruction-level parallelism: apply_pair() runs the arithmetic of the two particles of a
+// pair as one branch-free block (FusedWork) in which nothing is written to shared memory, and
+// only then performs the read-modify-writes -- one contiguous window per grid and particle:
+//   j2 (first)   D0+1 slots at the old cell
+//   j1           D1+2 slots starting at min(cell_old, cell_new): the old-cell and new-cell
+//                segments of add_current_update_v! merged, so the same window also gives
+//                v2 -= q/m sum(window * B)
+//   j2 (second)  D0+1 slots at the wrapped new position
+// Particles that move more than one cell (or sit outside one period) take the general
+// per-particle code (apply) instead.
+template <int D0, int D1>
+struct FusedWork {
+    double x, v1, v2;
+    int g0, gw, g0n;
+    bool slow;
+    double d2a[D0 + 1], dj1[D1 + 2], d2b[D0 + 1];
+};
+
+// (c - D) mod n for c - D in [-n, 2n)
+__device__ __forceinline__ int wrap_near(int g, int n)
+{
+    g = g < 0 ? g + n : g;
+    return g >= n ? g - n : g;
+}
+
 template <int D0, int D1, int NHE>
 struct OpStrangFused {
     static constexpr int READ = ROW_X | ROW_V1 | ROW_V2 | ROW_W, WRITE = ROW_X | ROW_V1 | ROW_V2;
     static constexpr int NF = 2 * NHE + 1, NG = 3, NS = 0;
     static constexpr bool DEPOSIT = true;
+    static constexpr bool PAIRWISE = true;
     struct Params { double dtqm_e[2], dtqm_p2, dt, qm_dx, wscale0, wscale1_dx; };
+    using PP = PassParams<OpStrangFused>;
+
+    // general per-particle form (any displacement)
     template <bool LP>
-    static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpStrangFused> &P, const double *sf,
-                                                 const Acc<LP> &acc)
+    static __device__ __forceinline__ void apply(Particle &p, const PP &P, const double *sf, const Acc<LP> &acc)
     {
         const int nh = P.m.n + kHalo;
         const double *sb = sf + 2 * NHE * nh;
@@ -234,6 +264,156 @@ struct OpStrangFused {
         basis_pp<D1>(pn.t, b1);
         basis_pp<D0>(pn.t, b0);
         push_p2<D0, D1, LP>(p, g0, g1, b0, b1, sb, P.op.dtqm_p2, ws0, acc, 2 * nh);
+    }
+
+    template <bool LP>
+    static __device__ __noinline__ void apply_general(Particle &p, const PP &P, const double *sf, const Acc<LP> &acc)
+    {
+        apply<LP>(p, P, sf, acc);
+    }
+
+    // branch-free arithmetic of one particle; no shared-memory writes
+    static __device__ __forceinline__ FusedWork<D0, D1> work(const Particle &p, const PP &P, const double *sf)
+    {
+        FusedWork<D0, D1> W;
+        const int n = P.m.n, nh = n + kHalo;
+        const double *sb = sf + 2 * NHE * nh;
+        double v1 = p.v1, v2 = p.v2;
+        // ---- HE kick(s) and first Hp2 at the old position
+        const Pos po = locate(p.x, P.m);
+        const int g0 = wrap_near(po.c - D0, n);
+        const int g1 = (D1 == D0) ? g0 : wrap_next(g0 + (D0 - D1), n);
+        double b1[D1 + 1], b0[D0 + 1];
+        basis_pp<D1>(po.t, b1);
+        basis_pp<D0>(po.t, b0);
+#pragma unroll
+        for (int h = 0; h < NHE; ++h) {
+            v1 = fma(P.op.dtqm_e[h], gather_h<D1>(sf + 2 * h * nh, g1, b1), v1);
+            v2 = fma(P.op.dtqm_e[h], gather_h<D0>(sf + (2 * h + 1) * nh, g0, b0), v2);
+        }
+        v1 = fma(P.op.dtqm_p2 * v2, gather_h<D1>(sb, g1, b1), v1);
+        const double ws0 = p.w * P.op.wscale0;
+        {
+            const double t2 = ws0 * v2;
+#pragma unroll
+            for (int k = 0; k <= D0; ++k) W.d2a[k] = t2 * b0[k];
+        }
+        W.g0 = g0;
+        // ---- Hp1: line integral over x -> x_new, old- and new-cell segments in one window
+        const double x_new = fma(P.op.dt, v1, p.x);
+        const Pos pn = locate(x_new, P.m);
+        double A[D1 + 1], B[D1 + 1];
+        prim_pp<D1>(po.t, A);
+        prim_pp<D1>(pn.t, B);
+        const bool same = pn.c == po.c, fwd = pn.c > po.c, bwd = pn.c < po.c;
+        double so[D1 + 1], sn[D1 + 1];
+#pragma unroll
+        for (int k = 0; k <= D1; ++k) {
+            const double F = prim_full<D1>(k);
+            so[k] = (same ? B[k] : (fwd ? F : 0.0)) - A[k];
+            sn[k] = same ? 0.0 : (fwd ? B[k] : B[k] - F);
+        }
+        const int gw = wrap_near((bwd ? pn.c : po.c) - D1, n);
+        double bsum = 0.0;
+        const double ws1 = p.w * P.op.wscale1_dx;
+#pragma unroll
+        for (int m = 0; m <= D1 + 1; ++m) {
+            // forward / same: old segment at offset 0, new at 1; backward: old at 1, new at 0
+            const double so_a = m <= D1 ? so[m <= D1 ? m : 0] : 0.0, so_b = m >= 1 ? so[m >= 1 ? m - 1 : 0] : 0.0;
+            const double sn_a = m <= D1 ? sn[m <= D1 ? m : 0] : 0.0, sn_b = m >= 1 ? sn[m >= 1 ? m - 1 : 0] : 0.0;
+            const double win = bwd ? so_b + sn_a : so_a + sn_b;
+            bsum = fma(win, sb[gw + m], bsum);
+            W.dj1[m] = ws1 * win;
+        }
+        v2 = fma(-P.op.qm_dx, bsum, v2);
+        W.gw = gw;
+        // x = mod(x_new, Lx) for x_new within one period of the domain (:79)
+        const double L = P.m.Lx;
+        const double x = x_new < 0.0 ? x_new + L : (x_new >= L ? x_new - L : x_new);
+        // ---- second Hp2 at the wrapped new position
+        const Pos p2 = locate(x, P.m);
+        const int g0n = wrap_near(p2.c - D0, n);
+        const int g1n = (D1 == D0) ? g0n : wrap_next(g0n + (D0 - D1), n);
+        basis_pp<D1>(p2.t, b1);
+        basis_pp<D0>(p2.t, b0);
+        v1 = fma(P.op.dtqm_p2 * v2, gather_h<D1>(sb, g1n, b1), v1);
+        {
+            const double t2 = ws0 * v2;
+#pragma unroll
+            for (int k = 0; k <= D0; ++k) W.d2b[k] = t2 * b0[k];
+        }
+        W.g0n = g0n;
+        W.x = x;
+        W.v1 = v1;
+        W.v2 = v2;
+        // fast-path domain: both cells within one cell of the grid, at most one boundary crossed
+        const unsigned span = (unsigned)(n + 2);
+        const int dc = pn.c - po.c;
+        W.slow = (unsigned)(po.c + 1) >= span || (unsigned)(pn.c + 1) >= span || dc > 1 || dc < -1 || n < 8;
+        return W;
+    }
+
+    // the three read-modify-write windows of one particle (lane-private slots: s -> s*32)
+    static __device__ __forceinline__ void commit(const FusedWork<D0, D1> &W, double *acc, int nh)
+    {
+        double *q0 = acc + (size_t)W.g0 * 32, *q1 = acc + (size_t)(nh + W.gw) * 32, *q2 = acc + (size_t)(2 * nh + W.g0n) * 32;
+        double r0[D0 + 1], r1[D1 + 2], r2[D0 + 1];
+#pragma unroll
+        for (int k = 0; k <= D0; ++k) r0[k] = q0[k * 32];
+#pragma unroll
+        for (int m = 0; m <= D1 + 1; ++m) r1[m] = q1[m * 32];
+#pragma unroll
+        for (int k = 0; k <= D0; ++k) r2[k] = q2[k * 32];
+#pragma unroll
+        for (int k = 0; k <= D0; ++k) q0[k * 32] = r0[k] + W.d2a[k];
+#pragma unroll
+        for (int m = 0; m <= D1 + 1; ++m) q1[m * 32] = r1[m] + W.dj1[m];
+#pragma unroll
+        for (int k = 0; k <= D0; ++k) q2[k * 32] = r2[k] + W.d2b[k];
+    }
+
+    template <bool LP>
+    static __device__ __forceinline__ void apply_pair(Particle &a, Particle &b, const PP &P, const double *sf, const Acc<LP> &acc)
+    {
+        const FusedWork<D0, D1> Wa = work(a, P, sf);
+        const FusedWork<D0, D1> Wb = work(b, P, sf);
+        if (__builtin_expect(Wa.slow | Wb.slow, 0)) {
+            apply_general<LP>(a, P, sf, acc);
+            apply_general<LP>(b, P, sf, acc);
+            return;
+        }
+        const int nh = P.m.n + kHalo;
+        commit(Wa, acc.p, nh);
+        commit(Wb, acc.p, nh);
+        a.x = Wa.x; a.v1 = Wa.v1; a.v2 = Wa.v2;
+        b.x = Wb.x; b.v1 = Wb.v1; b.v2 = Wb.v2;
+    }
+
+    // both batches of an iteration: four independent instruction streams before the commits
+    template <bool LP>
+    static __device__ __forceinline__ void apply_quad(Particle &a, Particle &b, Particle &c, Particle &d, const PP &P,
+                                                      const double *sf, const Acc<LP> &acc)
+    {
+        const FusedWork<D0, D1> Wa = work(a, P, sf);
+        const FusedWork<D0, D1> Wb = work(b, P, sf);
+        const FusedWork<D0, D1> Wc = work(c, P, sf);
+        const FusedWork<D0, D1> Wd = work(d, P, sf);
+        if (__builtin_expect(Wa.slow | Wb.slow | Wc.slow | Wd.slow, 0)) {
+            apply_general<LP>(a, P, sf, acc);
+            apply_general<LP>(b, P, sf, acc);
+            apply_general<LP>(c, P, sf, acc);
+            apply_general<LP>(d, P, sf, acc);
+            return;
+        }
+        const int nh = P.m.n + kHalo;
+        commit(Wa, acc.p, nh);
+        commit(Wb, acc.p, nh);
+        commit(Wc, acc.p, nh);
+        commit(Wd, acc.p, nh);
+        a.x = Wa.x; a.v1 = Wa.v1; a.v2 = Wa.v2;
+        b.x = Wb.x; b.v1 = Wb.v1; b.v2 = Wb.v2;
+        c.x = Wc.x; c.v1 = Wc.v1; c.v2 = Wc.v2;
+        d.x = Wd.x; d.v1 = Wd.v1; d.v2 = Wd.v2;
     }
 };
 

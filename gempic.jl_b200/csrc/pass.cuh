@@ -8,7 +8,7 @@
 // the deposit is run-to-run deterministic in LANE mode.
 //
 // Shared-memory layout
-//   fields        Op::NF vectors of n + kHalo doubles; the first kHalo dofs are repeated
+//   fields        Op::NF vectors of n + kHalo doubles; the first kHalo (= 4) dofs are repeated
 //                 after the last one so that a gather reads dofs g0 .. g0+D with ONE
 //                 periodic wrap per particle instead of one per dof.
 //   accumulators  Op::NG grids of n + kHalo slots (same halo trick; the halo is folded back
@@ -22,6 +22,8 @@
 //   ATOM mode  `copies` block-shared copies, warp w adds into copy w % copies with
 //              atomicAdd(double) on shared memory. Fallback for larger grids.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "splines.cuh"
 
@@ -29,7 +31,7 @@ namespace gempic {
 
 constexpr int kBlock = 128;  // threads per block (4 warps)
 constexpr int kWarps = kBlock / 32;
-constexpr int kHalo = kMaxDegree;
+constexpr int kHalo = kMaxDegree + 1;  // a degree-D stencil window shifted by one cell still fits (fused Hp1)
 constexpr int kMaxFields = 5;
 
 enum RowBits : int { ROW_X = 1, ROW_V1 = 2, ROW_V2 = 4, ROW_W = 8 };
@@ -103,6 +105,38 @@ __device__ __forceinline__ void store_one(const Rows &r, int64_t i, const Partic
     if (Op::WRITE & ROW_V2) r.v2[i] = a.v2;
 }
 
+// Ops may process the two particles of a pair jointly (Op::PAIRWISE + Op::apply_pair) so that the
+// arithmetic of both interleaves in one straight-line block; everything else goes one by one.
+template <class Op, class = void>
+struct is_pairwise : std::false_type {};
+template <class Op>
+struct is_pairwise<Op, std::enable_if_t<Op::PAIRWISE>> : std::true_type {};
+
+template <class Op, bool LP>
+__device__ __forceinline__ void apply2(Particle &a, Particle &b, const PassParams<Op> &P, const double *sf, const Acc<LP> &acc)
+{
+    if constexpr (is_pairwise<Op>::value && LP) {
+        Op::apply_pair(a, b, P, sf, acc);
+    } else {
+        Op::apply(a, P, sf, acc);
+        Op::apply(b, P, sf, acc);
+    }
+}
+
+template <class Op, bool LP>
+__device__ __forceinline__ void apply4(Particle &a0, Particle &a1, Particle &b0, Particle &b1, const PassParams<Op> &P,
+                                       const double *sf, const Acc<LP> &acc)
+{
+    if constexpr (is_pairwise<Op>::value && LP) {
+        Op::apply_quad(a0, a1, b0, b1, P, sf, acc);
+    } else {
+        Op::apply(a0, P, sf, acc);
+        Op::apply(a1, P, sf, acc);
+        Op::apply(b0, P, sf, acc);
+        Op::apply(b1, P, sf, acc);
+    }
+}
+
 template <class Op, bool LP>
 __global__ void __launch_bounds__(kBlock) k_pass(const __grid_constant__ PassParams<Op> P)
 {
@@ -150,11 +184,8 @@ __global__ void __launch_bounds__(kBlock) k_pass(const __grid_constant__ PassPar
                 load_pair<Op>(P.r, q, c0, c1);
                 load_pair<Op>(P.r, q + T, d0, d1);
             }
-            Op::apply(a0, P, sfield, acc);
-            Op::apply(a1, P, sfield, acc);
+            apply4<Op, LP>(a0, a1, b0, b1, P, sfield, acc);
             store_pair<Op>(P.r, p, a0, a1);
-            Op::apply(b0, P, sfield, acc);
-            Op::apply(b1, P, sfield, acc);
             store_pair<Op>(P.r, p + T, b0, b1);
             a0 = c0; a1 = c1; b0 = d0; b1 = d1;
             p = q;
@@ -165,19 +196,15 @@ __global__ void __launch_bounds__(kBlock) k_pass(const __grid_constant__ PassPar
             Particle a0, a1, b0, b1;
             load_pair<Op>(P.r, p, a0, a1);
             load_pair<Op>(P.r, p + T, b0, b1);
-            Op::apply(a0, P, sfield, acc);
-            Op::apply(a1, P, sfield, acc);
+            apply4<Op, LP>(a0, a1, b0, b1, P, sfield, acc);
             store_pair<Op>(P.r, p, a0, a1);
-            Op::apply(b0, P, sfield, acc);
-            Op::apply(b1, P, sfield, acc);
             store_pair<Op>(P.r, p + T, b0, b1);
         }
     }
     for (; p < n_pairs; p += T) {
         Particle a0, a1;
         load_pair<Op>(P.r, p, a0, a1);
-        Op::apply(a0, P, sfield, acc);
-        Op::apply(a1, P, sfield, acc);
+        apply2<Op, LP>(a0, a1, P, sfield, acc);
         store_pair<Op>(P.r, p, a0, a1);
     }
     if ((P.n_particles & 1) && blockIdx.x == 0 && tid == 0) {
