@@ -135,6 +135,19 @@ static void fused_pass(Splitting &h, double dt, int n_he)
     field_copy(h.j2(), h.acc() + 2 * h.n, h.n);
 }
 
+// The fused pass only pays while its three lane-private grids fit in shared memory (n <~ 35 cells at
+// degree 3); larger grids run one pass per reference operator.
+static bool fused_fits(Splitting &h)
+{
+    bool ok = false;
+    GP_DISPATCH_DEGREES(h.ks0->degree, h.ks1->degree, {
+        using Op = OpStrangFused<D0, D1, 2>;
+        auto P = base_params<Op>(h);
+        ok = plan_pass(P).lane_private;
+    });
+    return ok;
+}
+
 // strang_splitting! (hamiltonian_splitting.jl:98-108) with the particle passes fused.
 // Per step the reference runs HB HE Hp2 Hp1 Hp2 HE HB (each dt/2 except Hp1).  Field-only work
 // is hoisted around two kinds of particle pass:
@@ -228,7 +241,7 @@ static void strang_step(Splitting &h, double dt)
 void hs_strang(Splitting &h, double dt, int64_t steps)
 {
     if (steps <= 0) return;
-    if (h.fuse && h.V == 2) {
+    if (h.fuse && h.V == 2 && fused_fits(h)) {
         strang_fused(h, dt, steps);
         return;
     }

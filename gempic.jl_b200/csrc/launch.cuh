@@ -18,6 +18,7 @@ struct PartialScratch {
 // keeps >= 2 blocks (8 warps) resident per SM.
 constexpr size_t kLanePrivateMaxBytes = 110 * 1024;
 constexpr size_t kSmemBudget = 200 * 1024;
+constexpr size_t kSmemMaxOptin = 232448;   // 227 KB: largest dynamic shared memory of one sm_100 block
 
 struct LaunchInfo {
     int grid = 0;
@@ -30,15 +31,18 @@ template <class Op>
 inline LaunchInfo plan_pass(const PassParams<Op> &P)
 {
     LaunchInfo L;
-    const size_t field_bytes = (size_t)Op::NF * (P.m.n + kHalo) * sizeof(double);
+    constexpr int kNW = op_threads<Op>::value / 32;
+    const size_t field_bytes = (size_t)Op::NF * (P.m.n + op_halo<Op>::value) * op_field_copies<Op>::value * sizeof(double);
     if (!Op::DEPOSIT) {
         L.lane_private = true;
         L.smem = field_bytes;
         return L;
     }
     const size_t one = (size_t)acc_slots<Op>(P.m.n) * sizeof(double);
-    const size_t lp = one * 32 * kWarps;
-    if (field_bytes + lp <= kLanePrivateMaxBytes) {
+    const size_t lp = one * 32 * kNW;
+    // 128-thread ops keep two blocks per SM; a 256-thread op is planned as one block per SM
+    const size_t lp_max = op_threads<Op>::value > 128 ? kSmemMaxOptin : kLanePrivateMaxBytes;
+    if (field_bytes + lp <= lp_max) {
         L.lane_private = true;
         L.smem = field_bytes + lp;
     } else {
@@ -46,7 +50,7 @@ inline LaunchInfo plan_pass(const PassParams<Op> &P)
                    "deposit grid of %d dofs does not fit in shared memory", acc_outputs<Op>(P.m.n));
         size_t copies = (kSmemBudget / 2 - field_bytes) / one;
         if (copies < 1) copies = 1;
-        if (copies > (size_t)kWarps) copies = kWarps;
+        if (copies > (size_t)kNW) copies = kNW;
         L.lane_private = false;
         L.copies = (int)copies;
         L.smem = field_bytes + copies * one;
@@ -64,7 +68,7 @@ inline int configure_kernel(size_t smem)
         configured = smem;
     }
     int per_sm = 0;
-    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
+    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, op_threads<Op>::value, smem));
     return per_sm;
 }
 
@@ -84,15 +88,16 @@ inline void launch_pass(PassParams<Op> P, PartialScratch *scratch, double *out, 
     GP_REQUIRE(per_sm >= 1, GEMPIC_EINVAL, "pass does not fit on an SM (smem %zu B)", L.smem);
     int grid = c.sm_count * per_sm;
     const int64_t pairs = (P.n_particles + 1) / 2;
-    const int64_t need = (pairs + kBlock - 1) / kBlock;
+    constexpr int kThreads = op_threads<Op>::value;
+    const int64_t need = (pairs + kThreads - 1) / kThreads;
     if (need < grid) grid = (int)need;
     P.copies = L.copies;
     if (Op::DEPOSIT) P.partials = scratch->ensure((size_t)grid * n_out);
     if (tag) profile_begin(tag);
     if (L.lane_private)
-        k_pass<Op, true><<<grid, kBlock, L.smem, c.stream>>>(P);
+        k_pass<Op, true><<<grid, kThreads, L.smem, c.stream>>>(P);
     else
-        k_pass<Op, false><<<grid, kBlock, L.smem, c.stream>>>(P);
+        k_pass<Op, false><<<grid, kThreads, L.smem, c.stream>>>(P);
     GP_CUDA(cudaGetLastError());
     if (tag) profile_end(tag);
     count_launch();

@@ -200,17 +200,23 @@ struct OpHp1 {
 // performs all four: 32 B read + 24 B written per particle instead of 4 passes (168 B).
 // NHE = 2 additionally folds in the trailing HE of the previous step (fields e1T, e2T), which
 // is separated from this step's leading HE only by field-only updates.
-//   fields: [e1, e2] x NHE, b      grids: j2 (first Hp2), j1, j2 (second Hp2)
+//   source fields: [e1, e2] x NHE, b      grids: j2 (first Hp2), j1, j2 (second Hp2)
 //
-// Three lane-private grids leave room for only 8 warps per SM, so the pass lives on
-// instruction-level parallelism: apply_pair() runs the arithmetic of the two particles of a
-// pair as one branch-free block (FusedWork) in which nothing is written to shared memory, and
-// only then performs the read-modify-writes -- one contiguous window per grid and particle:
-//   j2 (first)   D0+1 slots at the old cell
-//   j1           D1+2 slots starting at min(cell_old, cell_new): the old-cell and new-cell
-//                segments of add_current_update_v! merged, so the same window also gives
-//                v2 -= q/m sum(window * B)
-//   j2 (second)  D0+1 slots at the wrapped new position
+// What bounds this pass is the shared-memory pipe (ncu r01c: l1tex data-pipe wavefronts 96 % of
+// peak, a third of them bank conflicts of the field gathers), so it is laid out to minimise
+// wavefronts:
+//   * the kicks of all NHE electric fields are linear in the dofs, so the staged fields are
+//     E1 = sum_h dt_h q/m e1^(h) and E2 likewise: NHE kicks cost one gather each;
+//   * every staged dof exists in 16 lane-interleaved copies (Op::FIELD_COPIES): a gather is
+//     conflict free for any cell pattern;
+//   * deposits are read-modify-writes of lane-private grids (pass.cuh), one contiguous window
+//     per grid and particle, issued after the branch-free arithmetic of a whole quad:
+//       j2 (first)   D0+1 slots at the old cell
+//       j1           D1+2 slots starting at min(cell_old, cell_new): the old-cell and new-cell
+//                    segments of add_current_update_v! merged, so the same window also gives
+//                    v2 -= q/m sum(window * B)
+//       j2 (second)  D0+1 slots at the wrapped new position
+//   * one block of 8 warps per SM: 8 x 3 lane-private grids + the field copies = 223 KB.
 // Particles that move more than one cell (or sit outside one period) take the general
 // per-particle code (apply) instead.
 template <int D0, int D1>
@@ -228,70 +234,150 @@ __device__ __forceinline__ int wrap_near(int g, int n)
     return g >= n ? g - n : g;
 }
 
+// sum_k field[k * S] * b[k]  (field points at the first dof of the stencil, copy stride S)
+template <int D, int S>
+__device__ __forceinline__ double gather_s(const double *__restrict__ field, const double (&b)[D + 1])
+{
+    double v = field[0] * b[0];
+#pragma unroll
+    for (int k = 1; k <= D; ++k) v = fma(field[k * S], b[k], v);
+    return v;
+}
+
 template <int D0, int D1, int NHE>
 struct OpStrangFused {
     static constexpr int READ = ROW_X | ROW_V1 | ROW_V2 | ROW_W, WRITE = ROW_X | ROW_V1 | ROW_V2;
-    static constexpr int NF = 2 * NHE + 1, NG = 3, NS = 0;
+    static constexpr int NSRC = 2 * NHE + 1;   // global field vectors in PassParams::fields
+    static constexpr int NF = 3, NG = 3, NS = 0;   // staged: E1, E2, b
     static constexpr bool DEPOSIT = true;
     static constexpr bool PAIRWISE = true;
+    static constexpr int THREADS = 256;
+    static constexpr int FIELD_COPIES = 16;
+    static constexpr int HALO = (D0 > D1 + 1) ? D0 : D1 + 1;   // widest window minus one
+    static constexpr bool CUSTOM_STAGE = true;
+    static constexpr int FC = FIELD_COPIES;
     struct Params { double dtqm_e[2], dtqm_p2, dt, qm_dx, wscale0, wscale1_dx; };
     using PP = PassParams<OpStrangFused>;
 
-    // general per-particle form (any displacement)
+    // staged fields (each dof in FC copies, periodic halo appended):
+    //   0: sum_h dtqm_e[h] e1^(h)     1: sum_h dtqm_e[h] e2^(h)     2: b
+    static __device__ __forceinline__ void stage(const PP &P, double *sfield, int tid)
+    {
+        const int n = P.m.n, nh = n + HALO;
+        for (int i = tid; i < nh; i += THREADS) {
+            const int g = i < n ? i : i - n;
+            double c1 = P.op.dtqm_e[0] * P.fields[0][g], c2 = P.op.dtqm_e[0] * P.fields[1][g];
+            if (NHE == 2) {
+                c1 = fma(P.op.dtqm_e[1], P.fields[2][g], c1);
+                c2 = fma(P.op.dtqm_e[1], P.fields[3][g], c2);
+            }
+            const double bb = P.fields[2 * NHE][g];
+#pragma unroll
+            for (int c = 0; c < FC; ++c) {
+                sfield[(size_t)i * FC + c] = c1;
+                sfield[(size_t)(nh + i) * FC + c] = c2;
+                sfield[(size_t)(2 * nh + i) * FC + c] = bb;
+            }
+        }
+    }
+
+    // general per-particle form (any displacement); sf already points at this lane's field copy
     template <bool LP>
     static __device__ __forceinline__ void apply(Particle &p, const PP &P, const double *sf, const Acc<LP> &acc)
     {
-        const int nh = P.m.n + kHalo;
-        const double *sb = sf + 2 * NHE * nh;
+        const int nh = P.m.n + HALO;
+        const double *se1 = sf, *se2 = sf + (size_t)nh * FC, *sb = sf + (size_t)2 * nh * FC;
         Pos ps = locate(p.x, P.m);
         int g0, g1;
         first_dofs<D0, D1>(ps, P.m, g0, g1);
         double b1[D1 + 1], b0[D0 + 1];
         basis_pp<D1>(ps.t, b1);
         basis_pp<D0>(ps.t, b0);
-#pragma unroll
-        for (int h = 0; h < NHE; ++h) kick_e<D0, D1>(p, g0, g1, b0, b1, sf + 2 * h * nh, sf + (2 * h + 1) * nh, P.op.dtqm_e[h]);
+        p.v1 += gather_s<D1, FC>(se1 + g1 * FC, b1);
+        p.v2 += gather_s<D0, FC>(se2 + g0 * FC, b0);
         const double ws0 = p.w * P.op.wscale0;
-        push_p2<D0, D1, LP>(p, g0, g1, b0, b1, sb, P.op.dtqm_p2, ws0, acc, 0);
-        // Hp1
+        p.v1 = fma(P.op.dtqm_p2 * p.v2, gather_s<D1, FC>(sb + g1 * FC, b1), p.v1);
+        deposit_h<D0, LP>(acc, g0, b0, ws0 * p.v2);
+        // Hp1: add_current_update_v! cell by cell
         const double x_new = fma(P.op.dt, p.v1, p.x);
         Pos pn = locate(x_new, P.m);
-        p.v2 = current_update_v<D1, LP, true>(acc, nh, sb, ps, pn, p.w * P.op.wscale1_dx, P.op.qm_dx, p.v2, P.m);
+        {
+            double A[D1 + 1], B[D1 + 1];
+            prim_pp<D1>(ps.t, A);
+            prim_pp<D1>(pn.t, B);
+            const bool same = ps.c == pn.c, fwd = ps.c < pn.c;
+            const double ws_dx = p.w * P.op.wscale1_dx;
+            double bsum = 0.0;
+            int g = first_dof<D1>(ps, P.m);
+#pragma unroll
+            for (int k = 0; k <= D1; ++k) {
+                const double s = (same ? B[k] : (fwd ? prim_full<D1>(k) : 0.0)) - A[k];
+                acc.add(nh + g + k, ws_dx * s);
+                bsum = fma(s, sb[(g + k) * FC], bsum);
+            }
+            if (!same) {
+                g = first_dof<D1>(pn, P.m);
+#pragma unroll
+                for (int k = 0; k <= D1; ++k) {
+                    const double s = fwd ? B[k] : B[k] - prim_full<D1>(k);
+                    acc.add(nh + g + k, ws_dx * s);
+                    bsum = fma(s, sb[(g + k) * FC], bsum);
+                }
+                const int lo = fwd ? ps.c : pn.c, hi = fwd ? pn.c : ps.c;
+                for (int c = lo + 1; c < hi; ++c) {
+                    g = wrap_index(c - D1, P.m);
+#pragma unroll
+                    for (int k = 0; k <= D1; ++k) {
+                        const double s = fwd ? prim_full<D1>(k) : -prim_full<D1>(k);
+                        acc.add(nh + g + k, ws_dx * s);
+                        bsum = fma(s, sb[(g + k) * FC], bsum);
+                    }
+                }
+            }
+            p.v2 = fma(-P.op.qm_dx, bsum, p.v2);
+        }
         p.x = mod_julia(x_new, P.m.Lx);
         if (p.x != x_new) pn = locate(p.x, P.m);
         // second Hp2 at the new position
         first_dofs<D0, D1>(pn, P.m, g0, g1);
         basis_pp<D1>(pn.t, b1);
         basis_pp<D0>(pn.t, b0);
-        push_p2<D0, D1, LP>(p, g0, g1, b0, b1, sb, P.op.dtqm_p2, ws0, acc, 2 * nh);
+        p.v1 = fma(P.op.dtqm_p2 * p.v2, gather_s<D1, FC>(sb + g1 * FC, b1), p.v1);
+        deposit_h<D0, LP>(acc, 2 * nh + g0, b0, ws0 * p.v2);
     }
 
+    // out of line and by value, so that the rare call does not pin the particles of the fast
+    // path to local memory
+    struct XV { double x, v1, v2; };
     template <bool LP>
-    static __device__ __noinline__ void apply_general(Particle &p, const PP &P, const double *sf, const Acc<LP> &acc)
+    static __device__ __noinline__ XV apply_general(double x, double v1, double v2, double w, const PP &P, const double *sf,
+                                                    double *accp)
     {
+        Particle p{x, v1, v2, w};
+        Acc<LP> acc{accp};
         apply<LP>(p, P, sf, acc);
+        return XV{p.x, p.v1, p.v2};
     }
 
     // branch-free arithmetic of one particle; no shared-memory writes
     static __device__ __forceinline__ FusedWork<D0, D1> work(const Particle &p, const PP &P, const double *sf)
     {
         FusedWork<D0, D1> W;
-        const int n = P.m.n, nh = n + kHalo;
-        const double *sb = sf + 2 * NHE * nh;
+        const int n = P.m.n, nh = n + HALO;
+        const double *se1 = sf, *se2 = sf + (size_t)nh * FC, *sb = sf + (size_t)2 * nh * FC;
         double v1 = p.v1, v2 = p.v2;
         // ---- HE kick(s) and first Hp2 at the old position
         const Pos po = locate(p.x, P.m);
         const int g0 = wrap_near(po.c - D0, n);
         const int g1 = (D1 == D0) ? g0 : wrap_next(g0 + (D0 - D1), n);
-        double b1[D1 + 1], b0[D0 + 1];
+        double A[D1 + 1], b1[D1 + 1], b0[D0 + 1];
+        prim_pp<D1>(po.t, A);
         basis_pp<D1>(po.t, b1);
-        basis_pp<D0>(po.t, b0);
-#pragma unroll
-        for (int h = 0; h < NHE; ++h) {
-            v1 = fma(P.op.dtqm_e[h], gather_h<D1>(sf + 2 * h * nh, g1, b1), v1);
-            v2 = fma(P.op.dtqm_e[h], gather_h<D0>(sf + (2 * h + 1) * nh, g0, b0), v2);
-        }
-        v1 = fma(P.op.dtqm_p2 * v2, gather_h<D1>(sb, g1, b1), v1);
+        if constexpr (D1 == D0 - 1) basis_from_prim<D0>(A, b0);
+        else basis_pp<D0>(po.t, b0);
+        v1 += gather_s<D1, FC>(se1 + g1 * FC, b1);
+        v2 += gather_s<D0, FC>(se2 + g0 * FC, b0);
+        v1 = fma(P.op.dtqm_p2 * v2, gather_s<D1, FC>(sb + g1 * FC, b1), v1);
         const double ws0 = p.w * P.op.wscale0;
         {
             const double t2 = ws0 * v2;
@@ -299,30 +385,27 @@ struct OpStrangFused {
             for (int k = 0; k <= D0; ++k) W.d2a[k] = t2 * b0[k];
         }
         W.g0 = g0;
-        // ---- Hp1: line integral over x -> x_new, old- and new-cell segments in one window
+        // ---- Hp1: line integral over x -> x_new.  Window of D1+2 dofs from cmin = min(cells);
+        // with Phi_m(s, t) = int of spline m from the window start to (cell cmin+s, offset t):
+        //   Phi_m(0, t) = P_m(t) [m <= D1]          Phi_m(1, t) = P_m(1) [m <= D1] + P_{m-1}(t) [m >= 1]
+        // the weight of dof m is Phi_m(new) - Phi_m(old)   (= the per-cell sums of pmc1d.jl:316-373)
         const double x_new = fma(P.op.dt, v1, p.x);
         const Pos pn = locate(x_new, P.m);
-        double A[D1 + 1], B[D1 + 1];
-        prim_pp<D1>(po.t, A);
+        double B[D1 + 1];
         prim_pp<D1>(pn.t, B);
-        const bool same = pn.c == po.c, fwd = pn.c > po.c, bwd = pn.c < po.c;
-        double so[D1 + 1], sn[D1 + 1];
-#pragma unroll
-        for (int k = 0; k <= D1; ++k) {
-            const double F = prim_full<D1>(k);
-            so[k] = (same ? B[k] : (fwd ? F : 0.0)) - A[k];
-            sn[k] = same ? 0.0 : (fwd ? B[k] : B[k] - F);
-        }
-        const int gw = wrap_near((bwd ? pn.c : po.c) - D1, n);
+        const int cmin = min(po.c, pn.c);
+        const bool o1 = po.c != cmin, n1 = pn.c != cmin;
+        const int gw = wrap_near(cmin - D1, n);
         double bsum = 0.0;
         const double ws1 = p.w * P.op.wscale1_dx;
 #pragma unroll
         for (int m = 0; m <= D1 + 1; ++m) {
-            // forward / same: old segment at offset 0, new at 1; backward: old at 1, new at 0
-            const double so_a = m <= D1 ? so[m <= D1 ? m : 0] : 0.0, so_b = m >= 1 ? so[m >= 1 ? m - 1 : 0] : 0.0;
-            const double sn_a = m <= D1 ? sn[m <= D1 ? m : 0] : 0.0, sn_b = m >= 1 ? sn[m >= 1 ? m - 1 : 0] : 0.0;
-            const double win = bwd ? so_b + sn_a : so_a + sn_b;
-            bsum = fma(win, sb[gw + m], bsum);
+            const double F = m <= D1 ? prim_full<D1>(m <= D1 ? m : 0) : 0.0;
+            const double n0 = m <= D1 ? B[m <= D1 ? m : 0] : 0.0, o0 = m <= D1 ? A[m <= D1 ? m : 0] : 0.0;
+            const double nn = m == 0 ? F : (m <= D1 ? F + B[m >= 1 ? m - 1 : 0] : B[D1]);
+            const double oo = m == 0 ? F : (m <= D1 ? F + A[m >= 1 ? m - 1 : 0] : A[D1]);
+            const double win = (n1 ? nn : n0) - (o1 ? oo : o0);
+            bsum = fma(win, sb[(gw + m) * FC], bsum);
             W.dj1[m] = ws1 * win;
         }
         v2 = fma(-P.op.qm_dx, bsum, v2);
@@ -336,7 +419,7 @@ struct OpStrangFused {
         const int g1n = (D1 == D0) ? g0n : wrap_next(g0n + (D0 - D1), n);
         basis_pp<D1>(p2.t, b1);
         basis_pp<D0>(p2.t, b0);
-        v1 = fma(P.op.dtqm_p2 * v2, gather_h<D1>(sb, g1n, b1), v1);
+        v1 = fma(P.op.dtqm_p2 * v2, gather_s<D1, FC>(sb + g1n * FC, b1), v1);
         {
             const double t2 = ws0 * v2;
 #pragma unroll
@@ -373,16 +456,23 @@ struct OpStrangFused {
     }
 
     template <bool LP>
+    static __device__ __forceinline__ void general(Particle &a, const PP &P, const double *sf, const Acc<LP> &acc)
+    {
+        const XV r = apply_general<LP>(a.x, a.v1, a.v2, a.w, P, sf, acc.p);
+        a.x = r.x; a.v1 = r.v1; a.v2 = r.v2;
+    }
+
+    template <bool LP>
     static __device__ __forceinline__ void apply_pair(Particle &a, Particle &b, const PP &P, const double *sf, const Acc<LP> &acc)
     {
         const FusedWork<D0, D1> Wa = work(a, P, sf);
         const FusedWork<D0, D1> Wb = work(b, P, sf);
         if (__builtin_expect(Wa.slow | Wb.slow, 0)) {
-            apply_general<LP>(a, P, sf, acc);
-            apply_general<LP>(b, P, sf, acc);
+            general<LP>(a, P, sf, acc);
+            general<LP>(b, P, sf, acc);
             return;
         }
-        const int nh = P.m.n + kHalo;
+        const int nh = P.m.n + HALO;
         commit(Wa, acc.p, nh);
         commit(Wb, acc.p, nh);
         a.x = Wa.x; a.v1 = Wa.v1; a.v2 = Wa.v2;
@@ -399,13 +489,13 @@ struct OpStrangFused {
         const FusedWork<D0, D1> Wc = work(c, P, sf);
         const FusedWork<D0, D1> Wd = work(d, P, sf);
         if (__builtin_expect(Wa.slow | Wb.slow | Wc.slow | Wd.slow, 0)) {
-            apply_general<LP>(a, P, sf, acc);
-            apply_general<LP>(b, P, sf, acc);
-            apply_general<LP>(c, P, sf, acc);
-            apply_general<LP>(d, P, sf, acc);
+            general<LP>(a, P, sf, acc);
+            general<LP>(b, P, sf, acc);
+            general<LP>(c, P, sf, acc);
+            general<LP>(d, P, sf, acc);
             return;
         }
-        const int nh = P.m.n + kHalo;
+        const int nh = P.m.n + HALO;
         commit(Wa, acc.p, nh);
         commit(Wb, acc.p, nh);
         commit(Wc, acc.p, nh);

@@ -47,6 +47,30 @@ struct Particle {
     double x, v1, v2, w;
 };
 
+// ---- optional per-Op launch traits (defaults in parentheses) -------------------------------
+//   Op::THREADS       threads per block (kBlock)
+//   Op::HALO          periodic halo dofs of the shared field / accumulator vectors (kHalo)
+//   Op::FIELD_COPIES  lane-interleaved copies of every staged field dof (1).  With 16 copies a
+//                     half-warp's gather is bank-conflict free for ANY cell pattern: element
+//                     (dof i, copy c) sits at (i*16 + c) doubles and lane l reads copy l & 15.
+//   Op::stage(P, sfield, tid)   custom staging of the Op::NF shared field vectors
+template <class Op, class = void>
+struct op_threads { static constexpr int value = 128; };
+template <class Op>
+struct op_threads<Op, std::void_t<decltype(Op::THREADS)>> { static constexpr int value = Op::THREADS; };
+template <class Op, class = void>
+struct op_halo { static constexpr int value = kMaxDegree + 1; };
+template <class Op>
+struct op_halo<Op, std::void_t<decltype(Op::HALO)>> { static constexpr int value = Op::HALO; };
+template <class Op, class = void>
+struct op_field_copies { static constexpr int value = 1; };
+template <class Op>
+struct op_field_copies<Op, std::void_t<decltype(Op::FIELD_COPIES)>> { static constexpr int value = Op::FIELD_COPIES; };
+template <class Op, class = void>
+struct op_has_stage : std::false_type {};
+template <class Op>
+struct op_has_stage<Op, std::void_t<decltype(Op::CUSTOM_STAGE)>> : std::true_type {};
+
 template <bool LP>
 struct Acc {
     double *p;  // LP: warp base + lane ; ATOM: base of this warp's copy
@@ -70,7 +94,7 @@ struct PassParams {
 
 // slots of one accumulator copy / doubles of one reduced output vector
 template <class Op>
-__host__ __device__ constexpr int acc_slots(int n) { return Op::NG * (n + kHalo) + Op::NS; }
+__host__ __device__ constexpr int acc_slots(int n) { return Op::NG * (n + op_halo<Op>::value) + Op::NS; }
 template <class Op>
 __host__ __device__ constexpr int acc_outputs(int n) { return Op::NG * n + Op::NS; }
 
@@ -138,28 +162,39 @@ __device__ __forceinline__ void apply4(Particle &a0, Particle &a1, Particle &b0,
 }
 
 template <class Op, bool LP>
-__global__ void __launch_bounds__(kBlock) k_pass(const __grid_constant__ PassParams<Op> P)
+__global__ void __launch_bounds__(op_threads<Op>::value) k_pass(const __grid_constant__ PassParams<Op> P)
 {
+    constexpr int kThreads = op_threads<Op>::value, kNW = kThreads / 32, kH = op_halo<Op>::value,
+                  kFC = op_field_copies<Op>::value;
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
     const int n = P.m.n;
-    const int nh = n + kHalo;
+    const int nh = n + kH;
     // ---- stage the field dofs this op gathers from (with periodic halo) -------------------
     double *sfield = smem;
+    if constexpr (op_has_stage<Op>::value) {
+        Op::stage(P, sfield, tid);
+    } else {
 #pragma unroll
-    for (int f = 0; f < Op::NF; ++f)
-        for (int i = tid; i < nh; i += kBlock) sfield[f * nh + i] = P.fields[f][i < n ? i : i - n];
+        for (int f = 0; f < Op::NF; ++f)
+            for (int i = tid; i < nh; i += kThreads) {
+                const double v = P.fields[f][i < n ? i : i - n];
+#pragma unroll
+                for (int c = 0; c < kFC; ++c) sfield[(size_t)(f * nh + i) * kFC + c] = v;
+            }
+    }
     // ---- zero the block-private accumulators --------------------------------------------
-    double *sacc = smem + Op::NF * nh;
+    double *sacc = smem + (size_t)Op::NF * nh * kFC;
     const int slots = acc_slots<Op>(n);
-    const int acc_words = Op::DEPOSIT ? (LP ? slots * 32 * kWarps : slots * P.copies) : 0;
-    for (int i = tid; i < acc_words; i += kBlock) sacc[i] = 0.0;
+    const int acc_words = Op::DEPOSIT ? (LP ? slots * 32 * kNW : slots * P.copies) : 0;
+    for (int i = tid; i < acc_words; i += kThreads) sacc[i] = 0.0;
     __syncthreads();
 
     Acc<LP> acc;
     {
         const int warp = tid >> 5, lane = tid & 31;
         acc.p = LP ? sacc + (size_t)warp * slots * 32 + lane : sacc + (size_t)(warp % (P.copies > 0 ? P.copies : 1)) * slots;
+        if (kFC > 1) sfield += lane & (kFC - 1);
     }
 
     // ---- stream the particles: pairs, two batches per iteration -------------------------
@@ -167,8 +202,8 @@ __global__ void __launch_bounds__(kBlock) k_pass(const __grid_constant__ PassPar
     // registers are plentiful: the next iteration's rows are loaded before the current one is
     // processed (software prefetch), which hides the HBM latency those few warps cannot.
     const int64_t n_pairs = P.n_particles >> 1;
-    const int64_t T = (int64_t)gridDim.x * kBlock;
-    int64_t p = (int64_t)blockIdx.x * kBlock + tid;
+    const int64_t T = (int64_t)gridDim.x * kThreads;
+    int64_t p = (int64_t)blockIdx.x * kThreads + tid;
     if (Op::DEPOSIT) {
         Particle a0, a1, b0, b1;
         bool have = p + T < n_pairs;
@@ -219,19 +254,19 @@ __global__ void __launch_bounds__(kBlock) k_pass(const __grid_constant__ PassPar
         __syncthreads();
         const int n_out = acc_outputs<Op>(n);
         double *out = P.partials + (size_t)blockIdx.x * n_out;
-        for (int o = tid; o < n_out; o += kBlock) {
+        for (int o = tid; o < n_out; o += kThreads) {
             // output o -> first slot s0 (+ its halo image s1, or -1)
             int s0, s1 = -1;
             if (o < Op::NG * n) {
                 const int k = o / n, g = o - k * n;
                 s0 = k * nh + g;
-                if (g < kHalo) s1 = s0 + n;
+                if (g < kH) s1 = s0 + n;
             } else {
                 s0 = Op::NG * nh + (o - Op::NG * n);
             }
             double s = 0.0;
             if (LP) {
-                for (int w = 0; w < kWarps; ++w) {
+                for (int w = 0; w < kNW; ++w) {
                     const double *base = sacc + (size_t)w * slots * 32;
 #pragma unroll 8
                     for (int l = 0; l < 32; ++l) s += base[(size_t)s0 * 32 + ((l + o) & 31)];  // rotated: conflict free

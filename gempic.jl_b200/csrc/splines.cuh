@@ -89,6 +89,21 @@ __device__ __forceinline__ void prim_pp(double t, double (&P)[D + 1])
         P[3] = (((i24 * t) * t) * t) * t;
     }
 }
+// Degree-D pieces from the degree-(D-1) primitives at the same offset: d/dt N^D_k = N^{D-1}_{k-1} - N^{D-1}_k
+// (pieces numbered as in basis_pp / prim_pp), so  N^D_k(t) = N^D_k(0) + P_{k-1}(t) - P_k(t).
+// A pass that needs both prim_pp<D-1>(t) and basis_pp<D>(t) gets the latter for D DADDs.
+template <int D>
+__device__ __forceinline__ void basis_from_prim(const double (&P)[D], double (&b)[D + 1])
+{
+    static_assert(D >= 1, "degree");
+    // N^D_k(0): D=1 (1,0)  D=2 (1/2,1/2,0)  D=3 (1/6,4/6,1/6,0)
+    constexpr double at0[4][4] = {{1, 0, 0, 0}, {1, 0, 0, 0}, {0.5, 0.5, 0, 0}, {1.0 / 6.0, 4.0 / 6.0, 1.0 / 6.0, 0}};
+    b[0] = at0[D][0] - P[0];
+#pragma unroll
+    for (int k = 1; k < D; ++k) b[k] = (at0[D][k] + P[k - 1]) - P[k];
+    b[D] = P[D - 1];
+}
+
 // P_k(1): integral of piece k over its whole cell
 template <int D>
 __device__ __forceinline__ double prim_full(int k)
