@@ -30,6 +30,7 @@ class AssertionFailed(GempicError, AssertionError):
 
 
 FUNC1D = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
+FUNC2D = C.CFUNCTYPE(C.c_double, C.c_double, C.c_double, C.c_void_p)
 
 _lib = None
 

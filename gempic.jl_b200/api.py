@@ -11,10 +11,10 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import FUNC1D, c_handle, check, dptr
+from ._lib import FUNC1D, FUNC2D, c_handle, check, dptr
 
 __all__ = [
-    "OneDGrid", "TwoDGrid", "ParticleGroup", "ParticleMeshCoupling1D", "ParticleMeshCoupling2D", "Maxwell1DFEM",
+    "OneDGrid", "TwoDGrid", "ParticleGroup", "ParticleMeshCoupling1D", "ParticleMeshCoupling2D", "Maxwell1DFEM", "TwoDMaxwell",
     "HamiltonianSplitting", "HamiltonianSplittingBoris", "TimeHistoryDiagnostics", "strang_splitting",
     "staggering", "operatorHp1", "operatorHp2", "operatorHE", "operatorHB", "solve_poisson", "write_step",
     "add_charge", "evaluate", "add_current_update_v", "compute_e_from_rho", "compute_e_from_j", "compute_e_from_b",
@@ -390,6 +390,79 @@ class Maxwell1DFEM(_Handle):
     def l2projection(self, coefs_dofs, func, degree):
         cb = FUNC1D(lambda x, _ctx: float(func(x)))
         check(_L().gempic_maxwell1d_l2projection(self._h, dptr(coefs_dofs), cb, None, C.c_int(degree)))
+
+
+class TwoDMaxwell(_Handle):
+    """TwoDMaxwell(mesh, degree) (src/maxwell_2d_fem.jl:11-87); field vectors are lists of three flat
+    nx*ny arrays, x fastest, like the reference's `efield`, `bfield`."""
+
+    _destroy = "gempic_maxwell2d_destroy"
+
+    def __init__(self, mesh: TwoDGrid, degree: int):
+        super().__init__()
+        check(_L().gempic_maxwell2d_create(_f(mesh.xmin), _f(mesh.xmax), C.c_int(mesh.nx), _f(mesh.ymin), _f(mesh.ymax),
+                                           C.c_int(mesh.ny), C.c_int(degree), C.byref(self._h)))
+        self.mesh = mesh
+        self.nx, self.ny = mesh.nx, mesh.ny
+        self.n_dofs = mesh.nx * mesh.ny
+        self.s_deg_0, self.s_deg_1 = degree, degree - 1
+
+    def _table(self, which, axis):
+        out, cnt = np.zeros(max(self.nx, self.ny) + 8), C.c_int()
+        check(_L().gempic_maxwell2d_get_table(self._h, C.c_int(which), C.c_int(axis), dptr(out), C.byref(cnt)))
+        return out[:cnt.value].copy()
+
+    mass_line_0 = property(lambda s: [s._table(0, 0), s._table(0, 1)])
+    mass_line_1 = property(lambda s: [s._table(1, 0), s._table(1, 1)])
+
+    def compute_e_from_rho(self, efield, rho):
+        check(_L().gempic_maxwell2d_compute_e_from_rho(self._h, dptr(efield[0]), dptr(efield[1]), dptr(_vec(rho, self.n_dofs, "rho"))))
+
+    def compute_e_from_b(self, e, dt, b):
+        v = [_vec(x, self.n_dofs, "b") for x in b]
+        check(_L().gempic_maxwell2d_compute_e_from_b(self._h, dptr(e[0]), dptr(e[1]), dptr(e[2]), _f(dt), dptr(v[0]), dptr(v[1]), dptr(v[2])))
+
+    def compute_b_from_e(self, b, dt, e):
+        v = [_vec(x, self.n_dofs, "e") for x in e]
+        check(_L().gempic_maxwell2d_compute_b_from_e(self._h, dptr(b[0]), dptr(b[1]), dptr(b[2]), _f(dt), dptr(v[0]), dptr(v[1]), dptr(v[2])))
+
+    def compute_e_from_j(self, e, current, component):
+        check(_L().gempic_maxwell2d_compute_e_from_j(self._h, dptr(e), dptr(_vec(current, self.n_dofs, "current")), C.c_int(component)))
+
+    def compute_rho_from_e(self, rho, efield):
+        v = [_vec(x, self.n_dofs, "efield") for x in efield]
+        check(_L().gempic_maxwell2d_compute_rho_from_e(self._h, dptr(rho), dptr(v[0]), dptr(v[1]), dptr(v[2])))
+
+    def inner_product(self, coefs1_dofs, coefs2_dofs, component, form):
+        out = C.c_double()
+        check(_L().gempic_maxwell2d_inner_product(self._h, dptr(_vec(coefs1_dofs, self.n_dofs, "coefs1")),
+                                                  dptr(_vec(coefs2_dofs, self.n_dofs, "coefs2")), C.c_int(component),
+                                                  C.c_int(form), C.byref(out)))
+        return out.value
+
+    def solve_mass(self, rhs, component, form):
+        """solve(solver.inv_mass_1[component] | inv_mass_2[component], rhs)"""
+        out = np.zeros(self.n_dofs)
+        check(_L().gempic_maxwell2d_solve_mass(self._h, dptr(out), dptr(_vec(rhs, self.n_dofs, "rhs")), C.c_int(component), C.c_int(form)))
+        return out
+
+    def multiply_mass(self, c_in, component, form):
+        """multiply_mass_2dkron! with the mass lines of (component, form)"""
+        out = np.zeros(self.n_dofs)
+        check(_L().gempic_maxwell2d_multiply_mass(self._h, dptr(out), dptr(_vec(c_in, self.n_dofs, "c_in")), C.c_int(component), C.c_int(form)))
+        return out
+
+    def compute_rhs_from_function(self, func, component, form):
+        out = np.zeros(self.n_dofs)
+        cb = FUNC2D(lambda x, y, _ctx: float(func(x, y)))
+        check(_L().gempic_maxwell2d_compute_rhs_from_function(self._h, dptr(out), cb, None, C.c_int(component), C.c_int(form)))
+        return out
+
+    def l2projection(self, func, component, form):
+        out = np.zeros(self.n_dofs)
+        cb = FUNC2D(lambda x, y, _ctx: float(func(x, y)))
+        check(_L().gempic_maxwell2d_l2projection(self._h, dptr(out), cb, None, C.c_int(component), C.c_int(form)))
+        return out
 
 
 class HamiltonianSplitting(_Handle):

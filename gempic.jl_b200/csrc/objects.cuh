@@ -82,6 +82,36 @@ void field_axpby(double *y, double a, const double *x, double b, int n);   // y 
 void field_copy(double *dst, const double *src, int n);
 void field_max_abs_diff(const double *a, const double *b, int n, double *out);
 
+// TwoDMaxwell (src/maxwell_2d_fem.jl:11-87) with its TwoDPoisson and TwoDLinearSolverSplineMass
+// members.  Index [d][a]: spline family d (0: s_deg_0, 1: s_deg_1) along axis a (0: x, 1: y).
+struct Maxwell2D : Object {
+    static constexpr Kind kKind = Kind::Maxwell2D;
+    static constexpr int kWork = 12;
+    int nx, ny, s_deg_0, s_deg_1;
+    double xmin, ymin, Lx, Ly, dx, dy;
+    std::vector<double> line[2][2];   // mass_line_0 / mass_line_1 scaled by dx, dy (:36-42)
+    std::vector<double> eig[2][2];    // spline_fem_compute_mass_eig of those lines (:51-54)
+    DevBuf<double> tab;               // device tables, offsets below
+    size_t off_inv[2][2], off_line[2][2], off_cos[2], off_sin[2], off_dre[2], off_dim[2], off_dtm[2], off_m0[2];
+    DevBuf<double> work;              // kWork scratch vectors of nx*ny
+    Maxwell2D() : Object(kKind) {}
+    const double *inv_col(int d, int a) const { return tab.p + off_inv[d][a]; }
+    const double *mass_line(int d, int a) const { return tab.p + off_line[d][a]; }
+    double *wk(int i) const { return work.p + (size_t)i * nx * ny; }
+};
+std::unique_ptr<Maxwell2D> make_maxwell2d(double xmin, double xmax, int nx, double ymin, double ymax, int ny, int degree);
+// device-pointer field operators (fields2d.cu); `deg[c]` = spline family along (x, y) of component c
+void m2d_form_degrees(int component, int form, int out[2]);
+void m2d_solve_mass(const Maxwell2D &m, int njobs, const int (*deg)[2], const double *const *in, double *const *out,
+                    const double *const *base, int mode, double scale);
+void m2d_multiply_mass(const Maxwell2D &m, int njobs, const int (*deg)[2], const double *const *in, double *const *out);
+void m2d_e_from_j(const Maxwell2D &m, double *e, const double *j, int component);
+void m2d_e_from_b(const Maxwell2D &m, double *const e[3], double dt, const double *const b[3]);
+void m2d_b_from_e(const Maxwell2D &m, double *const b[3], double dt, const double *const e[3]);
+void m2d_rho_from_e(const Maxwell2D &m, double *rho, const double *const e[3]);
+void m2d_e_from_rho(const Maxwell2D &m, double *e1, double *e2, const double *rho);
+void m2d_inner_product(const Maxwell2D &m, const double *c1, const double *c2, int component, int form, double *out);
+
 // HamiltonianSplitting{1,2}/{1,1} (src/hamiltonian_splitting.jl:20-86)
 struct Splitting : Object {
     static constexpr Kind kKind = Kind::Splitting;

@@ -154,6 +154,34 @@ int gempic_maxwell1d_compute_rhs_from_function(gempic_handle m, double *coefs, g
                                                int degree);                                       /* :188-220 */
 int gempic_maxwell1d_l2projection(gempic_handle m, double *coefs, gempic_func1d f, void *ctx, int degree); /* :347-374 */
 
+/* ---- TwoDMaxwell (src/maxwell_2d_fem.jl:11-87) with TwoDPoisson (src/poisson_2d_fem.jl) and
+ *      TwoDLinearSolverSplineMass (src/linear_solver_spline_mass_2d.jl) ---------------------
+ * dofs are flat nx*ny vectors, x fastest.  component is 1-based, form in 0..3 (:136-149). */
+int gempic_maxwell2d_create(double xmin, double xmax, int nx, double ymin, double ymax, int ny, int degree,
+                            gempic_handle *out);
+int gempic_maxwell2d_destroy(gempic_handle m);
+/* which: 0 mass_line_0, 1 mass_line_1, 2 eig_values_mass_0, 3 eig_values_mass_1; axis 0 (x) / 1 (y) */
+int gempic_maxwell2d_get_table(gempic_handle m, int which, int axis, double *out, int *count);
+int gempic_maxwell2d_compute_e_from_rho(gempic_handle m, double *e1, double *e2, const double *rho);   /* :199-201, poisson :237-262 */
+int gempic_maxwell2d_compute_e_from_b(gempic_handle m, double *e1, double *e2, double *e3, double dt,
+                                      const double *b1, const double *b2, const double *b3);         /* :370-412 */
+int gempic_maxwell2d_compute_b_from_e(gempic_handle m, double *b1, double *b2, double *b3, double dt,
+                                      const double *e1, const double *e2, const double *e3);         /* :423-444 */
+int gempic_maxwell2d_compute_e_from_j(gempic_handle m, double *e, const double *current, int component); /* :455-459 */
+int gempic_maxwell2d_compute_rho_from_e(gempic_handle m, double *rho, const double *e1, const double *e2,
+                                        const double *e3);                                            /* :468-500 */
+int gempic_maxwell2d_inner_product(gempic_handle m, const double *c1, const double *c2, int component, int form,
+                                   double *out);                                                      /* :512-575 */
+/* solve(inv_mass_1[component] | inv_mass_2[component], rhs)  (linear_solver_spline_mass_2d.jl:16-32) */
+int gempic_maxwell2d_solve_mass(gempic_handle m, double *out, const double *rhs, int component, int form);
+/* multiply_mass_2dkron! with the mass lines of (component, form)  (:343-363) */
+int gempic_maxwell2d_multiply_mass(gempic_handle m, double *out, const double *in, int component, int form);
+typedef double (*gempic_func2d)(double x, double y, void *ctx);
+int gempic_maxwell2d_compute_rhs_from_function(gempic_handle m, double *coefs, gempic_func2d f, void *ctx,
+                                               int component, int form);                              /* :124-196 */
+int gempic_maxwell2d_l2projection(gempic_handle m, double *coefs, gempic_func2d f, void *ctx, int component,
+                                  int form);                                                          /* :283-293 */
+
 /* ---- HamiltonianSplitting{1,2} / {1,1} (src/hamiltonian_splitting.jl:20-108) ---------- */
 int gempic_hs_create(int D, int V, gempic_handle maxwell, gempic_handle pmc0, gempic_handle pmc1,
                      gempic_handle pg, gempic_handle *out);

@@ -14,6 +14,7 @@ def declared_symbols():
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     names = set(re.findall(r"\b(gempic_[a-z0-9_]+)\s*\(", text))
     names.discard("gempic_func1d")
+    names.discard("gempic_func2d")
     return sorted(names)
 
 
