@@ -46,9 +46,27 @@ BETA = 1e-4
 NX = 32
 DT = 0.05
 DEG = 3
+# workloads: BASELINE.json configs[1] (default, the metric's config), configs[2] and configs[3] at one GPU's share
+WORKLOADS = {
+    "weibel": dict(name="Weibel instability 1d2v HamiltonianSplitting, 32 cells, deg 3/2 galerkin, dt 0.05 (BASELINE configs[1])",
+                   L=L_WEIBEL, sigma=SIGMA, kind="uniform", alpha=0.0, k=K_WEIBEL, integrator="hs"),
+    "landau": dict(name="strong Landau damping 1d2v HamiltonianSplitting, 32 cells, deg 3/2 galerkin, dt 0.05 (BASELINE configs[2])",
+                   L=4 * math.pi, sigma=(1.0, 1.0), kind="landau", alpha=0.5, k=0.5, integrator="hs"),
+    "boris": dict(name="Boris-splitting 1d2v push (HamiltonianSplittingBoris), strong Landau load, 32 cells, deg 3/2, dt 0.05 "
+                       "(BASELINE configs[3])",
+                  L=4 * math.pi, sigma=(1.0, 1.0), kind="landau", alpha=0.5, k=0.5, integrator="boris"),
+}
 # algorithmic DRAM bytes per particle of each pass (fp64 SoA rows x, v1, v2, w; SURVEY section 8d / DESIGN.md)
 BYTES = {"operatorHE": 40, "operatorHp2": 40, "operatorHp1": 48, "strang_step": 208,
-         "fused[HE,Hp2,Hp1,Hp2]": 56, "fused[HE,HE,Hp2,Hp1,Hp2]": 56}
+         "fused[HE,Hp2,Hp1,Hp2]": 56, "fused[HE,HE,Hp2,Hp1,Hp2]": 56, "boris_step": 56, "boris_strang_step": 56}
+
+
+def ncu_traffic(tag):
+    """dram bytes per particle of a pass from the committed `ncu --set full` capture (profiles/ncu_traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(tag)
+    except Exception:
+        return None
 
 
 def peaks():
@@ -111,36 +129,59 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
-def weibel_b0(mod, mx):
-    """B3(0) = beta cos(kx) through l2projection! (test_vm_1d2v.jl:33,80-84)"""
+def weibel_b0(mod, mx, wl=None):
+    """B3(0) = beta cos(kx) through l2projection! (test_vm_1d2v.jl:33,80-84); B = 0 for the Landau loads
+    (examples/strong_landau_damping_1d2v.jl:36-39)"""
     b = np.zeros(NX)
-    mx.l2projection(b, lambda x: BETA * math.cos(2 * math.pi * x / L_WEIBEL), DEG - 1)
+    if wl is None or wl["kind"] == "uniform":
+        mx.l2projection(b, lambda x: BETA * math.cos(2 * math.pi * x / L_WEIBEL), DEG - 1)
     return b
 
 
+def host_state(wl, n, rng):
+    """seeded host particle set of a workload (the CPU arm; the GPU arm samples on the device)"""
+    L = wl["L"]
+    st = np.empty((4, n))
+    if wl["kind"] == "uniform":
+        st[0] = rng.uniform(0, L, n)
+    else:   # inverse CDF of 1 + alpha cos(kx) by Newton (particle_sampling.jl:294-311)
+        u = rng.uniform(0, 1, n)
+        x = u * L
+        for _ in range(30):
+            x -= (x + wl["alpha"] / wl["k"] * np.sin(wl["k"] * x) - u * L) / (1 + wl["alpha"] * np.cos(wl["k"] * x))
+        st[0] = np.mod(x, L)
+    st[1] = wl["sigma"][0] * rng.normal(size=n)
+    st[2] = wl["sigma"][1] * rng.normal(size=n)
+    st[3] = L
+    return st
+
+
 # =============================== CPU reference arm ==============================================
-def cpu_reference(n_cpu: int, steps: int, warmup: int, threads: int | None = None):
-    """Times the oracle's strang_splitting (C restatement of src/hamiltonian_splitting_1d2v.jl,
+def cpu_reference(n_cpu: int, steps: int, warmup: int, threads: int | None = None, workload: str = "weibel"):
+    """Times the oracle's strang_splitting (C restatement of src/hamiltonian_splitting_1d2v.jl / _boris.jl,
     OpenMP over particle chunks with private deposit buffers like the reference's @spawn chunks)."""
     from oracle import oracle as orc
 
     orc.build()
+    wl = WORKLOADS[workload]
     cores = threads or orc.max_threads()
     n_cpu -= n_cpu % cores
     rng = np.random.default_rng(1234)
-    mesh = orc.OneDGrid(0.0, L_WEIBEL, NX)
+    mesh = orc.OneDGrid(0.0, wl["L"], NX)
     pg = orc.ParticleGroup(1, 2, n_cpu)
-    pg.array[0] = rng.uniform(0, L_WEIBEL, n_cpu)
-    pg.array[1] = SIGMA[0] * rng.normal(size=n_cpu)
-    pg.array[2] = SIGMA[1] * rng.normal(size=n_cpu)
-    pg.array[3] = L_WEIBEL
+    pg.array[:, :] = host_state(wl, n_cpu, rng)
     ks0 = orc.ParticleMeshCoupling1D(mesh, n_cpu, DEG, "galerkin")
     ks1 = orc.ParticleMeshCoupling1D(mesh, n_cpu, DEG - 1, "galerkin")
     mx = orc.Maxwell1DFEM(mesh, DEG)
     e1, e2, rho = np.zeros(NX), np.zeros(NX), np.zeros(NX)
-    b = weibel_b0(orc, mx)
+    b = weibel_b0(orc, mx, wl)
     orc.solve_poisson(e1, pg, ks0, mx, rho)
-    h = orc.HamiltonianSplitting(1, 2, mx, ks0, ks1, pg, [e1, e2], b, n_chunks=cores)
+    if wl["integrator"] == "boris":
+        h = orc.HamiltonianSplittingBoris(mx, ks0, ks1, pg, [e1, e2], b)
+        h.staggering(DT)
+        cores = 1   # the oracle's Boris loops are serial, like the reference's (hamiltonian_splitting_boris.jl:189-288)
+    else:
+        h = orc.HamiltonianSplitting(1, 2, mx, ks0, ks1, pg, [e1, e2], b, n_chunks=cores)
     for _ in range(warmup):
         h.strang_splitting(DT, 1)
     t0 = time.perf_counter()
@@ -148,7 +189,7 @@ def cpu_reference(n_cpu: int, steps: int, warmup: int, threads: int | None = Non
         h.strang_splitting(DT, 1)
     dt = time.perf_counter() - t0
     return {"value": n_cpu * steps / dt, "unit": "particle-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{n_cpu} particles x {steps} Strang steps (same Weibel 1d2v config), C restatement of the "
+            "sample": f"{n_cpu} particles x {steps} Strang steps (same {workload} 1d2v config), C restatement of the "
                       f"reference Julia path with OpenMP chunks -- Julia unavailable", "seconds": dt}, dt / steps
 
 
@@ -157,7 +198,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     n_cpu = args.cpu_particles
-    base, sec_per_step = cpu_reference(n_cpu, args.steps, args.warmup)
+    base, sec_per_step = cpu_reference(n_cpu, args.steps, args.warmup, workload=args.workload)
     line = {
         "impl": "reference", "metric": "particle-steps/s per Strang step", "value": base["value"], "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3,
@@ -167,17 +208,18 @@ def run_reference(args):
         "e2e": {"value": base["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
 def workload_config(args, n_per_gpu, note=None):
-    cfg = {"workload": "Weibel instability 1d2v HamiltonianSplitting, 32 cells, deg 3/2 galerkin, dt 0.05 "
-                       "(BASELINE configs[1])",
+    cfg = {"workload": WORKLOADS[args.workload]["name"],
            "particles_per_gpu": int(n_per_gpu), "n_cells": NX, "spline_degree": [DEG, DEG - 1], "dt": DT,
            "parallelism": f"particles sharded over {args.gpus} GPU(s), NCCL allreduce of rho/j",
            "l2_policy": "inputs (32 B/particle x N >> 126 MB L2) stream from HBM every pass; no flush needed",
-           "kernels": ("fused passes [HE,(HE,)Hp2,Hp1,Hp2] + HE, one strang_splitting!(h, dt, K) call" if args.fuse
+           "kernels": ("one fused pass per step [push_v_epart, push_v_bpart, push_v_epart, push_x_accumulate_j]"
+                       if WORKLOADS[args.workload]["integrator"] == "boris" else
+                       "fused passes [HE,(HE,)Hp2,Hp1,Hp2] + HE, one strang_splitting!(h, dt, K) call" if args.fuse
                        else "one pass per reference operator, K calls of strang_splitting!(h, dt, 1)")}
     if note:
         cfg["note"] = note
@@ -202,20 +244,28 @@ def run_ours(args):
     n_global = n_local * dc.world_size
     first = dc.rank * n_local
 
-    mesh = gp.OneDGrid(0.0, L_WEIBEL, NX)
+    wl = WORKLOADS[args.workload]
+    boris = wl["integrator"] == "boris"
+    Lw = wl["L"]
+    mesh = gp.OneDGrid(0.0, Lw, NX)
     pg = gp.ParticleGroup(1, 2, n_local, common_weight=1.0 / n_global)
-    pg.sample("uniform", 0.0, L_WEIBEL, sigma=SIGMA, seed=1234, first_index=first)
+    pg.sample(wl["kind"], 0.0, Lw, alpha=wl["alpha"], k=wl["k"], sigma=wl["sigma"], seed=1234, first_index=first)
     ks0 = gp.ParticleMeshCoupling1D(mesh, n_local, DEG, "galerkin")
     ks1 = gp.ParticleMeshCoupling1D(mesh, n_local, DEG - 1, "galerkin")
     mx = gp.Maxwell1DFEM(mesh, DEG)
     e1, e2, rho = np.zeros(NX), np.zeros(NX), np.zeros(NX)
-    b = weibel_b0(gp, mx)
+    b = weibel_b0(gp, mx, wl)
     gp.solve_poisson(e1, pg, ks0, mx, rho)
     total_charge = float(rho.sum())
 
-    h = gp.HamiltonianSplitting(1, 2, mx, ks0, ks1, pg, [e1, e2], b, resident=True)
-    if args.fuse:
-        h.set_fusion(True)
+    if boris:
+        h = gp.HamiltonianSplittingBoris(mx, ks0, ks1, pg, [e1, e2], b, resident=True)
+        h.staggering(DT)
+        args.fuse = 1   # strang_splitting!(h::HamiltonianSplittingBoris, dt, K) is one call of K fused passes
+    else:
+        h = gp.HamiltonianSplitting(1, 2, mx, ks0, ks1, pg, [e1, e2], b, resident=True)
+        if args.fuse:
+            h.set_fusion(True)
 
     stream = torch.cuda.ExternalStream(gp.stream_ptr(), device=torch.device("cuda", dc.local_rank))
 
@@ -268,9 +318,15 @@ def run_ours(args):
 
     # ---- e2e: host field buffers every step ---------------------------------------------------
     h.sync_fields()
-    h_host = gp.HamiltonianSplitting(1, 2, mx, ks0, ks1, pg, [e1, e2], b, resident=False)
-    if args.fuse:
-        h_host.set_fusion(True)
+    if boris:
+        # same object family, host-buffer entry point (gempic_boris_strang_splitting_host); the staggered mid fields
+        # live in the splitting object, so the host variant is re-staggered from the current state
+        h_host = gp.HamiltonianSplittingBoris(mx, ks0, ks1, pg, [e1, e2], b, resident=False)
+        h_host.staggering(DT)
+    else:
+        h_host = gp.HamiltonianSplitting(1, 2, mx, ks0, ks1, pg, [e1, e2], b, resident=False)
+        if args.fuse:
+            h_host.set_fusion(True)
     for _ in range(min(args.warmup, 3)):
         h_host.strang_splitting(DT, 1)
     e2e_steps = args.steps
@@ -286,7 +342,7 @@ def run_ours(args):
     # ---- sanity: the timed state is a real simulation -------------------------------------------
     rho2, ep = np.zeros(NX), np.zeros(NX)
     gp.solve_poisson(ep, pg, ks0, mx, rho2)
-    assert abs(rho2.sum() - L_WEIBEL) < 1e-9 * L_WEIBEL and abs(total_charge - L_WEIBEL) < 1e-9 * L_WEIBEL, \
+    assert abs(rho2.sum() - Lw) < 1e-9 * Lw and abs(total_charge - Lw) < 1e-9 * Lw, \
         "charge is not conserved -- the step did not do its work"
     assert np.all(np.isfinite(e1)) and np.all(np.isfinite(b))
 
@@ -297,17 +353,22 @@ def run_ours(args):
         if dom in prof and prof[dom][1] > 0:
             t_ms = prof[dom][0] / prof[dom][1]
             achieved = BYTES[dom] * n_local / (t_ms * 1e-3) / 1e9
+            tr = ncu_traffic(dom)
             roof = {"bound": "hbm", "kernel": f"k_pass<{dom}>", "achieved": achieved,
-                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": (tr["dram_bytes_per_particle"] * n_local if tr else None),
+                    "traffic_note": (f"bytes per launch = {tr['dram_bytes_per_particle']} B/particle (ncu dram__bytes_read+write, "
+                                     f"{tr['source']}) x {n_local} particles" if tr else None),
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_particle": BYTES[dom], "avg_launch_ms": t_ms,
                     "all_passes": {k: {"avg_ms": v[0] / max(v[1], 1), "launches": v[1],
                                        "GBps": BYTES.get(k, 0) * n_local / (v[0] / max(v[1], 1) * 1e-3) / 1e9 if v[1] else None}
                                    for k, v in prof.items()},
-                    "step_GBps_vs_208B": BYTES["strang_step"] * n_local / (ms_per_step * 1e-3) / 1e9}
+                    "step_GBps_vs_unfused_bytes": BYTES["boris_strang_step" if boris else "strang_step"] * n_local / (ms_per_step * 1e-3) / 1e9}
         n_cpu = args.cpu_particles
         cpu = None
         if args.gpus == 1 and not args.no_cpu:
-            cpu, _ = cpu_reference(n_cpu, args.cpu_steps, 1)
+            cpu, _ = cpu_reference(n_cpu, args.cpu_steps, 1, workload=args.workload)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line = {
             "metric": "particle-steps/s per Strang step", "value": value, "unit": "particle-steps/s", "n_gpus": dc.world_size,
@@ -316,15 +377,31 @@ def run_ours(args):
             "config": workload_config(args, n_local),
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 3 * NX * 8,
                     "d2h_bytes_per_step": 5 * NX * 8, "steps": e2e_steps,
-                    "what": "gempic_hs_strang_splitting_host: host e1,e2,b in, e1,e2,b,j1,j2 out, synchronous"},
+                    "what": ("gempic_boris_strang_splitting_host" if boris else "gempic_hs_strang_splitting_host") +
+                            ": host e1,e2,b in, e1,e2,b(,j1,j2) out, synchronous"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     dc.finalize()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    # Libraries below us (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on stdout,
+    # so everything else is routed to stderr and the JSON line goes to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -334,6 +411,7 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=4_000_000, help="bounded sample for the CPU arm")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="weibel", choices=sorted(WORKLOADS), help="weibel = BASELINE configs[1] (the metric's config)")
     ap.add_argument("--fuse", type=int, default=1, help="1: fused particle passes (default), 0: one kernel per reference operator")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
