@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import FUNC1D, FUNC2D, c_handle, check, dptr
 
 __all__ = [
-    "OneDGrid", "TwoDGrid", "ParticleGroup", "ParticleMeshCoupling1D", "ParticleMeshCoupling2D", "Maxwell1DFEM", "TwoDMaxwell",
+    "OneDGrid", "TwoDGrid", "ParticleGroup", "ParticleMeshCoupling1D", "ParticleMeshCoupling2D", "Maxwell1DFEM", "TwoDMaxwell", "HamiltonianSplitting2D3V",
     "HamiltonianSplitting", "HamiltonianSplittingBoris", "TimeHistoryDiagnostics", "strang_splitting",
     "staggering", "operatorHp1", "operatorHp2", "operatorHE", "operatorHB", "solve_poisson", "write_step",
     "add_charge", "evaluate", "add_current_update_v", "compute_e_from_rho", "compute_e_from_j", "compute_e_from_b",
@@ -199,8 +199,12 @@ class ParticleGroup(_Handle):
 
     # -- device-side extras -------------------------------------------------------------------
     def sort(self, pmc):
+        """cell sort on the mesh of a ParticleMeshCoupling1D (D = 1) or a TwoDMaxwell (D = 2)"""
         self._flush()
-        check(_L().gempic_pg_sort(self._h, pmc.handle))
+        if self.dims[0] == 2:
+            check(_L().gempic_pg_sort2d(self._h, pmc.handle))
+        else:
+            check(_L().gempic_pg_sort(self._h, pmc.handle))
         self._touched()
 
     def sample(self, kind, xmin, L, alpha=0.0, k=1.0, sigma=(1.0, 1.0, 1.0), seed=1234, first_index=0):
@@ -535,6 +539,111 @@ class HamiltonianSplitting(_Handle):
                                                        dptr(self.e_dofs[1]), dptr(self.b_dofs), dptr(self.j_dofs[0]),
                                                        dptr(self.j_dofs[1])))
         pg._touched()
+
+
+class HamiltonianSplitting2D3V(_Handle):
+    """HamiltonianSplitting{2,3}(maxwell_solver::TwoDMaxwell, particle_group::ParticleGroup{2,3}, e_dofs, b_dofs):
+    the integrator the reference leaves empty (src/hamiltonian_splitting_2d3v.jl), with the field names and
+    operator methods of src/hamiltonian_splitting.jl:20-108.  e_dofs / b_dofs are lists of three aliased
+    flat nx*ny arrays."""
+
+    _destroy = "gempic_hs2d_destroy"
+    OP_HP3 = 5
+
+    def __init__(self, maxwell_solver, particle_group, e_dofs, b_dofs, resident=False):
+        super().__init__()
+        self.maxwell_solver, self.particle_group = maxwell_solver, particle_group
+        check(_L().gempic_hs2d_create(maxwell_solver.handle, particle_group.handle, C.byref(self._h)))
+        n = maxwell_solver.n_dofs
+        self.n = n
+        self.e_dofs = [_check_alias(a, n) for a in e_dofs]
+        self.b_dofs = [_check_alias(a, n) for a in b_dofs]
+        assert len(self.e_dofs) == 3 and len(self.b_dofs) == 3
+        self.resident = resident
+        if resident:
+            self.upload_fields()
+
+    def _fp(self):
+        return [dptr(a) for a in self.e_dofs + self.b_dofs]
+
+    def upload_fields(self):
+        check(_L().gempic_hs2d_set_fields(self._h, *self._fp()))
+
+    def sync_fields(self):
+        check(_L().gempic_hs2d_get_fields(self._h, *self._fp(), None, None, None))
+
+    @property
+    def j_dofs(self):
+        out = [np.zeros(self.n) for _ in range(3)]
+        check(_L().gempic_hs2d_get_fields(self._h, None, None, None, None, None, None, dptr(out[0]), dptr(out[1]), dptr(out[2])))
+        return out
+
+    def set_sort_interval(self, interval: int):
+        check(_L().gempic_hs2d_set_sort_interval(self._h, C.c_int(interval)))
+
+    def _op(self, op, dt):
+        pg = self.particle_group
+        pg._flush()
+        if self.resident:
+            check(_L().gempic_hs2d_operator(self._h, C.c_int(op), _f(dt)))
+        else:
+            check(_L().gempic_hs2d_operator_host(self._h, C.c_int(op), _f(dt), *self._fp()))
+        pg._touched()
+
+    def operatorHp1(self, dt):
+        self._op(OP_HP1, dt)
+
+    def operatorHp2(self, dt):
+        self._op(OP_HP2, dt)
+
+    def operatorHp3(self, dt):
+        self._op(self.OP_HP3, dt)
+
+    def operatorHE(self, dt):
+        self._op(OP_HE, dt)
+
+    def operatorHB(self, dt):
+        self._op(OP_HB, dt)
+
+    def strang_splitting(self, dt, number_steps):
+        pg = self.particle_group
+        pg._flush()
+        if self.resident:
+            check(_L().gempic_hs2d_strang_splitting(self._h, _f(dt), C.c_int64(number_steps)))
+        else:
+            check(_L().gempic_hs2d_strang_splitting_host(self._h, _f(dt), C.c_int64(number_steps), *self._fp()))
+        pg._touched()
+
+    # -- diagnostics ------------------------------------------------------------------------------
+    def charge_density(self):
+        self.particle_group._flush()
+        rho = np.zeros(self.n)
+        check(_L().gempic_hs2d_charge_density(self._h, dptr(rho)))
+        return rho
+
+    def gauss_residual(self):
+        """compute_rho_from_e!(E) - rho(particles); constant in time (discrete Gauss law)"""
+        if self.resident:
+            self.sync_fields()
+        r = np.zeros(self.n)
+        self.maxwell_solver.compute_rho_from_e(r, self.e_dofs)
+        return r - self.charge_density()
+
+    def moments(self):
+        self.particle_group._flush()
+        out = np.zeros(4)
+        check(_L().gempic_hs2d_moments(self._h, dptr(out)))
+        return out
+
+    def energies(self):
+        """(kinetic, electric, magnetic) like TimeHistoryDiagnostics' KineticEnergy / PotentialEnergy columns"""
+        if self.resident:
+            self.sync_fields()
+        mx, pg = self.maxwell_solver, self.particle_group
+        kin = 0.5 * pg.mass * pg.common_weight * self.moments()[0]
+        ee = 0.5 * sum(mx.inner_product(self.e_dofs[c], self.e_dofs[c], c + 1, 1) for c in range(3))
+        eb = 0.5 * sum(mx.inner_product(self.b_dofs[c], self.b_dofs[c], c + 1, 2) for c in range(3))
+        return kin, ee, eb
 
 
 def _check_alias(a, n):

@@ -88,7 +88,7 @@ void h2d(double *dev, const double *host, size_t n);  // synchronous w.r.t. the 
 void d2h(double *host, const double *dev, size_t n);  // synchronises the library stream
 
 // ---- objects behind handles -----------------------------------------------------------
-enum class Kind : uint32_t { ParticleGroup = 1, Pmc1D, Pmc2D, Maxwell1D, Splitting, Boris, Maxwell2D };
+enum class Kind : uint32_t { ParticleGroup = 1, Pmc1D, Pmc2D, Maxwell1D, Splitting, Boris, Maxwell2D, Splitting2D };
 
 struct Object {
     Kind kind;

@@ -1,0 +1,798 @@
+// hs2d.cu -- HamiltonianSplitting{2,3}: the 2d3v Vlasov-Maxwell splitting on ParticleGroup{2,3} and
+// TwoDMaxwell (BASELINE config 5).
+//
+// GEMPIC.jl ships no 2d3v integrator (src/hamiltonian_splitting_2d3v.jl is an empty file); these
+// operators are the 2D extension of src/hamiltonian_splitting_1d2v.jl:41-236 on the reference's 2D
+// building blocks (tensor-product splines of particle_mesh_coupling_2d.jl, the mixed-degree spaces of
+// maxwell_2d_fem.jl), following the GEMPIC paper cited in CITATION.bib:
+//   HE   v += dt q/m E(x);  b -= dt curl e                      (1d2v.jl:191-219)
+//   HB   e += dt M1^-1 curl^T M2 b                              (:234-236)
+//   Hp1  x1 += dt v1;  j1 = line integral;  v2 -= q/m int B3 dx1;  v3 += q/m int B2 dx1   (:41-112)
+//   Hp2  x2 += dt v2;  j2 = line integral;  v1 += q/m int B3 dx2;  v3 -= q/m int B1 dx2
+//   Hp3  v1 -= dt q/m v3 B2;  v2 += dt q/m v3 B1;  j3 = w v3 N(x) dt                      (:129-176)
+//   strang_splitting!: HB HE Hp3 Hp2 Hp1 Hp2 Hp3 HE HB  (hamiltonian_splitting.jl:98-108 with the third
+//   velocity component added symmetrically)
+// Spaces (p = degree): E1 S^{p-1}xS^p, E2 S^pxS^{p-1}, E3 S^pxS^p; B1 S^pxS^{p-1}, B2 S^{p-1}xS^p,
+// B3 S^{p-1}xS^{p-1} (test/test_maxwell_2d_fem.jl:54-56,88-90).  Cells are floor((x-xmin)/dx).
+//
+// Kernel design (k2_pass).  A 64x64 grid is 32 KB per component: it cannot be privatised per lane like
+// the 1D grids.  Particles are kept cell-sorted (pg_sort_2d) and every warp streams a contiguous chunk
+// of them, so the dofs it touches lie in a small window around the cell of the chunk's first particle:
+//   * deposits go to a LANE-PRIVATE window tile in shared memory ((2R+1+p)^2 dofs, R = 3 cells of drift
+//     tolerance; slot s of lane l at (s*32 + l)*8 B): plain LDS/DADD/STS, no atomics, conflict free.  At
+//     the end of the chunk the 32 copies are summed and added to the global grid with one fp64 RED per
+//     dof.  Particles outside the window (never, while the sort is fresh) fall back to global REDs;
+//   * gathers read the field dofs straight from global memory: the lanes of a warp share (nearly) the
+//     same stencil, so every load is a broadcast hit in L1;
+//   * the next two particles of every lane are loaded before the current two are processed.
+#include <algorithm>
+
+#include "hostutil.hpp"
+#include "objects.cuh"
+
+namespace gempic {
+
+constexpr int kR2 = 3;          // window radius (cells) around the chunk's base cell
+constexpr int kWarps2 = 8;      // warps per block
+constexpr int kThreads2 = kWarps2 * 32;
+
+struct Mesh2 {
+    double xmin[2], d[2], inv_d[2], L[2], xmax[2];
+    int n[2];
+};
+
+struct Rows2 {
+    double *__restrict__ x[2];
+    double *__restrict__ v[3];
+    double *__restrict__ w;
+};
+
+struct Part2 {
+    double x[2], v[3], w;
+};
+
+__device__ __forceinline__ int wrapi(int g, int n)
+{
+    if (__builtin_expect((unsigned)(g + n) >= (unsigned)(3 * n), 0)) {
+        g %= n;
+        return g < 0 ? g + n : g;
+    }
+    g = g < 0 ? g + n : g;
+    return g >= n ? g - n : g;
+}
+
+template <int AX>
+__device__ __forceinline__ void locate2(double x, const Mesh2 &m, int &c, double &t)
+{
+    const double a = x - m.xmin[AX];
+    const double q = a * m.inv_d[AX];
+    const double r = fma(-q, m.d[AX], a);
+    const double xi = fma(r, m.inv_d[AX], q);   // correctly rounded a / d (see div_dx, splines.cuh)
+    c = __double2int_rd(xi);
+    t = xi - (double)c;
+}
+
+// relative cell offset of c (unwrapped, within one period of the box) to the wrapped base cell
+__device__ __forceinline__ int rel_cell(int c, int base, int n)
+{
+    int r = c - base;
+    const int h = n >> 1;
+    if (r > h) r -= n;
+    else if (r < -h) r += n;
+    return r;
+}
+
+// periodic dof indices of the degree-D0 stencil: idx[a] = (c - D0 + a) mod n.  The degree-(D0-1) stencil
+// of the same cell is idx[1..D0].
+template <int D0>
+__device__ __forceinline__ void stencil(int c, int n, int (&idx)[D0 + 1])
+{
+    int g = wrapi(c - D0, n);
+#pragma unroll
+    for (int a = 0; a <= D0; ++a) {
+        idx[a] = g;
+        g = g + 1 == n ? 0 : g + 1;
+    }
+}
+
+// sum_{a<=DX, b<=DY} f[ix[OX+a] + iy[OY+b]*nx] bx[a] by[b]
+template <int DX, int DY, int OX, int OY, int D0>
+__device__ __forceinline__ double eval2(const double *__restrict__ f, int nx, const int (&ix)[D0 + 1], const int (&iy)[D0 + 1],
+                                        const double (&bx)[DX + 1], const double (&by)[DY + 1])
+{
+    double v = 0.0;
+#pragma unroll
+    for (int b = 0; b <= DY; ++b) {
+        const double *row = f + (size_t)iy[OY + b] * nx;
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a <= DX; ++a) s = fma(__ldg(row + ix[OX + a]), bx[a], s);
+        v = fma(s, by[b], v);
+    }
+    return v;
+}
+
+template <class Op>
+struct P2 {
+    Rows2 r;
+    int64_t n;
+    int64_t chunk;
+    Mesh2 m;
+    const double *f[3];
+    double *grid;   // deposit target (nx*ny), zeroed by the launcher
+    typename Op::Params op;
+};
+
+template <int D0>
+struct Tile {
+    static constexpr int W = 2 * kR2 + 1 + D0;
+    static constexpr int SLOTS = W * W;
+};
+
+// ---- operatorHE: v += dt q/m E(x) -------------------------------------------------------------
+template <int D0>
+struct Op2HE {
+    static constexpr bool DEPOSIT = false, WRITE_X = false, WRITE_V = true;
+    static constexpr int D = D0;
+    struct Params { double dtqm; };
+    static __device__ __forceinline__ void apply(Part2 &p, const P2<Op2HE> &P, double *, int, int)
+    {
+        constexpr int D1 = D0 - 1;
+        int cx, cy, ix[D0 + 1], iy[D0 + 1];
+        double tx, ty, bx0[D0 + 1], bx1[D1 + 1], by0[D0 + 1], by1[D1 + 1];
+        locate2<0>(p.x[0], P.m, cx, tx);
+        locate2<1>(p.x[1], P.m, cy, ty);
+        stencil<D0>(cx, P.m.n[0], ix);
+        stencil<D0>(cy, P.m.n[1], iy);
+        basis_pp<D0>(tx, bx0); basis_pp<D1>(tx, bx1);
+        basis_pp<D0>(ty, by0); basis_pp<D1>(ty, by1);
+        const int nx = P.m.n[0];
+        p.v[0] = fma(P.op.dtqm, eval2<D1, D0, 1, 0, D0>(P.f[0], nx, ix, iy, bx1, by0), p.v[0]);
+        p.v[1] = fma(P.op.dtqm, eval2<D0, D1, 0, 1, D0>(P.f[1], nx, ix, iy, bx0, by1), p.v[1]);
+        p.v[2] = fma(P.op.dtqm, eval2<D0, D0, 0, 0, D0>(P.f[2], nx, ix, iy, bx0, by0), p.v[2]);
+    }
+};
+
+// (D0+1)^2 deposit of wv * bx0 (x) by0 at cell (cx, cy): lane-private tile or global fallback
+template <int D0>
+__device__ __forceinline__ void deposit_pp(double *tile, double *__restrict__ grid, const Mesh2 &m, int cx, int cy, int bx, int by,
+                                           const double (&wx)[D0 + 1], const double (&wy)[D0 + 1], double wv)
+{
+    constexpr int W = Tile<D0>::W;
+    const int rx = rel_cell(cx, bx, m.n[0]), ry = rel_cell(cy, by, m.n[1]);
+    if (__builtin_expect(rx >= -kR2 && rx <= kR2 && ry >= -kR2 && ry <= kR2, 1)) {
+        double *q = tile + (size_t)((ry + kR2) * W + rx + kR2) * 32;
+#pragma unroll
+        for (int b = 0; b <= D0; ++b) {
+            const double wb = wv * wy[b];
+            double r[D0 + 1];
+#pragma unroll
+            for (int a = 0; a <= D0; ++a) r[a] = q[(b * W + a) * 32];
+#pragma unroll
+            for (int a = 0; a <= D0; ++a) q[(b * W + a) * 32] = fma(wb, wx[a], r[a]);
+        }
+    } else {
+        int ix[D0 + 1], iy[D0 + 1];
+        stencil<D0>(cx, m.n[0], ix);
+        stencil<D0>(cy, m.n[1], iy);
+        for (int b = 0; b <= D0; ++b)
+            for (int a = 0; a <= D0; ++a) atomicAdd(grid + ix[a] + (size_t)iy[b] * m.n[0], (wv * wy[b]) * wx[a]);
+    }
+}
+
+// ---- add_charge!: rho += q w N^p(x1) N^p(x2) ----------------------------------------------------
+template <int D0>
+struct Op2Charge {
+    static constexpr bool DEPOSIT = true, WRITE_X = false, WRITE_V = false;
+    static constexpr int D = D0;
+    struct Params { double wscale; };
+    static __device__ __forceinline__ void apply(Part2 &p, const P2<Op2Charge> &P, double *tile, int bx, int by)
+    {
+        int cx, cy;
+        double tx, ty, bx0[D0 + 1], by0[D0 + 1];
+        locate2<0>(p.x[0], P.m, cx, tx);
+        locate2<1>(p.x[1], P.m, cy, ty);
+        basis_pp<D0>(tx, bx0);
+        basis_pp<D0>(ty, by0);
+        deposit_pp<D0>(tile, P.grid, P.m, cx, cy, bx, by, bx0, by0, p.w * P.op.wscale);
+    }
+};
+
+// ---- operatorHp3: v1 -= dt q/m v3 B2, v2 += dt q/m v3 B1, j3 += q w v3 dt N N ------------------
+template <int D0>
+struct Op2Hp3 {
+    static constexpr bool DEPOSIT = true, WRITE_X = false, WRITE_V = true;
+    static constexpr int D = D0;
+    struct Params { double dtqm, wscale_dt; };   // fields: f[0] = B1, f[1] = B2
+    static __device__ __forceinline__ void apply(Part2 &p, const P2<Op2Hp3> &P, double *tile, int bx, int by)
+    {
+        constexpr int D1 = D0 - 1;
+        int cx, cy, ix[D0 + 1], iy[D0 + 1];
+        double tx, ty, bx0[D0 + 1], bx1[D1 + 1], by0[D0 + 1], by1[D1 + 1];
+        locate2<0>(p.x[0], P.m, cx, tx);
+        locate2<1>(p.x[1], P.m, cy, ty);
+        stencil<D0>(cx, P.m.n[0], ix);
+        stencil<D0>(cy, P.m.n[1], iy);
+        basis_pp<D0>(tx, bx0); basis_pp<D1>(tx, bx1);
+        basis_pp<D0>(ty, by0); basis_pp<D1>(ty, by1);
+        const int nx = P.m.n[0];
+        const double B1 = eval2<D0, D1, 0, 1, D0>(P.f[0], nx, ix, iy, bx0, by1);
+        const double B2 = eval2<D1, D0, 1, 0, D0>(P.f[1], nx, ix, iy, bx1, by0);
+        const double v3 = p.v[2];
+        p.v[0] = fma(-(P.op.dtqm * v3), B2, p.v[0]);
+        p.v[1] = fma(P.op.dtqm * v3, B1, p.v[1]);
+        deposit_pp<D0>(tile, P.grid, P.m, cx, cy, bx, by, bx0, by0, (p.w * P.op.wscale_dt) * v3);
+    }
+};
+
+// ---- operatorHp1 (DIR = 0) / operatorHp2 (DIR = 1) ------------------------------------------------
+// f[0] = B3, f[1] = B2 (DIR 0) or B1 (DIR 1).  Along DIR the degree-(p-1) splines are integrated over the
+// straight path x_old -> x_new (primitive form, splines.cuh prim_pp; window of p+1 dofs from the lower cell
+// as in OpStrangFused); across DIR the degree-p (j, B2/B1) and degree-(p-1) (B3) splines are evaluated.
+template <int D0, int DIR>
+struct Op2Hp12 {
+    static constexpr bool DEPOSIT = true, WRITE_X = true, WRITE_V = true;
+    static constexpr int D = D0;
+    struct Params { double dt, qm_h, wscale_h; };   // h = d[DIR]
+    using PP = P2<Op2Hp12>;
+
+    // general path: any displacement, global REDs (rare: more than one cell per step or outside the window)
+    struct Sums { double z, o; };
+    static __device__ __noinline__ Sums general(double x_old, double x_new, int ct, const double *bt0, const double *bt1,
+                                               const PP &P, double wq)
+    {
+        double sum_z = 0.0, sum_o = 0.0;
+        constexpr int D1 = D0 - 1, O = 1 - DIR;
+        const Mesh2 &m = P.m;
+        int co, cn;
+        double to, tn;
+        locate2<DIR>(x_old, m, co, to);
+        locate2<DIR>(x_new, m, cn, tn);
+        const int step = cn >= co ? 1 : -1;
+        for (int c = co;; c += step) {
+            double lower, upper, sgn;
+            if (co == cn) { lower = to; upper = tn; sgn = 1.0; }
+            else if (step > 0) { lower = (c == co) ? to : 0.0; upper = (c == cn) ? tn : 1.0; sgn = 1.0; }
+            else { lower = (c == cn) ? tn : 0.0; upper = (c == co) ? to : 1.0; sgn = -1.0; }
+            double Pl[D1 + 1], Pu[D1 + 1];
+            prim_pp<D1>(lower, Pl);
+            prim_pp<D1>(upper, Pu);
+            for (int k = 0; k <= D1; ++k) {
+                const double s = sgn * (Pu[k] - Pl[k]);
+                const int ia = wrapi(c - D1 + k, m.n[DIR]);
+                for (int b = 0; b <= D0; ++b) {
+                    const int it = wrapi(ct - D0 + b, m.n[O]);
+                    const size_t idx = DIR == 0 ? (size_t)ia + (size_t)it * m.n[0] : (size_t)it + (size_t)ia * m.n[0];
+                    atomicAdd(P.grid + idx, wq * s * bt0[b]);
+                    sum_o += P.f[1][idx] * s * bt0[b];
+                }
+                for (int b = 0; b <= D1; ++b) {
+                    const int it = wrapi(ct - D1 + b, m.n[O]);
+                    const size_t idx = DIR == 0 ? (size_t)ia + (size_t)it * m.n[0] : (size_t)it + (size_t)ia * m.n[0];
+                    sum_z += P.f[0][idx] * s * bt1[b];
+                }
+            }
+            if (c == cn) break;
+        }
+        return Sums{sum_z, sum_o};
+    }
+
+    static __device__ __forceinline__ void apply(Part2 &p, const PP &P, double *tile, int bx, int by)
+    {
+        constexpr int D1 = D0 - 1, O = 1 - DIR, W = Tile<D0>::W;
+        const Mesh2 &m = P.m;
+        const double x_old = p.x[DIR], x_new = fma(P.op.dt, p.v[DIR], x_old);
+        int co, cn, ct;
+        double to, tn, tt;
+        locate2<DIR>(x_old, m, co, to);
+        locate2<DIR>(x_new, m, cn, tn);
+        locate2<O>(p.x[O], m, ct, tt);
+        double bt0[D0 + 1], bt1[D1 + 1];
+        basis_pp<D0>(tt, bt0);
+        basis_pp<D1>(tt, bt1);
+        const double wq = p.w * P.op.wscale_h;
+        double sum_z = 0.0, sum_o = 0.0;
+        const int base_d = DIR == 0 ? bx : by, base_t = DIR == 0 ? by : bx;
+        const int ro = rel_cell(co, base_d, m.n[DIR]), rn = rel_cell(cn, base_d, m.n[DIR]), rt = rel_cell(ct, base_t, m.n[O]);
+        const int dc = cn - co;
+        // the window of D1+2 dofs starts at local index rmin + kR2 + 1: cells up to kR2 - 1 keep it inside the tile
+        const bool fast = dc >= -1 && dc <= 1 && ro >= -kR2 && ro < kR2 && rn >= -kR2 && rn < kR2 && rt >= -kR2 && rt <= kR2;
+        if (__builtin_expect(fast, 1)) {
+            // window of D1+2 dofs from cmin (see OpStrangFused::work): weight_m = Phi_m(new) - Phi_m(old)
+            double A[D1 + 1], B[D1 + 1], win[D1 + 2];
+            prim_pp<D1>(to, A);
+            prim_pp<D1>(tn, B);
+            const int cmin = min(co, cn);
+            const bool o1 = co != cmin, n1 = cn != cmin;
+#pragma unroll
+            for (int k = 0; k <= D1 + 1; ++k) {
+                const double F = k <= D1 ? prim_full<D1>(k <= D1 ? k : 0) : 0.0;
+                const double n0 = k <= D1 ? B[k <= D1 ? k : 0] : 0.0, o0 = k <= D1 ? A[k <= D1 ? k : 0] : 0.0;
+                const double nn = k == 0 ? F : (k <= D1 ? F + B[k >= 1 ? k - 1 : 0] : B[D1]);
+                const double oo = k == 0 ? F : (k <= D1 ? F + A[k >= 1 ? k - 1 : 0] : A[D1]);
+                win[k] = (n1 ? nn : n0) - (o1 ? oo : o0);
+            }
+            // periodic indices: along DIR the window, across DIR the degree-D0 stencil
+            int iw[D1 + 2], it[D0 + 1];
+            {
+                int g = wrapi(cmin - D1, m.n[DIR]);
+#pragma unroll
+                for (int k = 0; k <= D1 + 1; ++k) {
+                    iw[k] = g;
+                    g = g + 1 == m.n[DIR] ? 0 : g + 1;
+                }
+            }
+            stencil<D0>(ct, m.n[O], it);
+            const int nx = m.n[0];
+            const int sd = DIR == 0 ? 1 : nx, st = DIR == 0 ? nx : 1;   // strides along / across DIR
+            // gathers: B3 (transverse D1: it[1..D0]) and the other component (transverse D0)
+#pragma unroll
+            for (int k = 0; k <= D1 + 1; ++k) {
+                double sz = 0.0, so = 0.0;
+#pragma unroll
+                for (int b = 0; b <= D1; ++b) sz = fma(__ldg(P.f[0] + (size_t)iw[k] * sd + (size_t)it[b + 1] * st), bt1[b], sz);
+#pragma unroll
+                for (int b = 0; b <= D0; ++b) so = fma(__ldg(P.f[1] + (size_t)iw[k] * sd + (size_t)it[b] * st), bt0[b], so);
+                sum_z = fma(sz, win[k], sum_z);
+                sum_o = fma(so, win[k], sum_o);
+            }
+            // deposit j[window x stencil]: local window start = rmin + kR2 + 1 (degree D1 = D0-1), stencil rt + kR2
+            const int rmin = min(ro, rn);
+            const int lw = rmin + kR2 + (D0 - D1), lt = rt + kR2;
+            double *q = tile + (size_t)(DIR == 0 ? lt * W + lw : lw * W + lt) * 32;
+            constexpr int qd = (DIR == 0 ? 1 : W) * 32, qt = (DIR == 0 ? W : 1) * 32;
+#pragma unroll
+            for (int b = 0; b <= D0; ++b) {
+                const double wb = wq * bt0[b];
+                double r[D1 + 2];
+#pragma unroll
+                for (int k = 0; k <= D1 + 1; ++k) r[k] = q[b * qt + k * qd];
+#pragma unroll
+                for (int k = 0; k <= D1 + 1; ++k) q[b * qt + k * qd] = fma(wb, win[k], r[k]);
+            }
+        } else {
+            const Sums g = general(x_old, x_new, ct, bt0, bt1, P, wq);
+            sum_z = g.z;
+            sum_o = g.o;
+        }
+        if (DIR == 0) {
+            p.v[1] = fma(-P.op.qm_h, sum_z, p.v[1]);
+            p.v[2] = fma(P.op.qm_h, sum_o, p.v[2]);
+        } else {
+            p.v[0] = fma(P.op.qm_h, sum_z, p.v[0]);
+            p.v[2] = fma(-P.op.qm_h, sum_o, p.v[2]);
+        }
+        double xw = x_new;
+        while (xw < m.xmin[DIR]) xw += m.L[DIR];
+        while (xw >= m.xmax[DIR]) xw -= m.L[DIR];
+        p.x[DIR] = xw;
+    }
+};
+
+template <class Op>
+__device__ __forceinline__ void load2(const Rows2 &r, int64_t i, Part2 &p)
+{
+    p.x[0] = r.x[0][i];
+    p.x[1] = r.x[1][i];
+    p.v[0] = r.v[0][i];
+    p.v[1] = r.v[1][i];
+    p.v[2] = r.v[2][i];
+    p.w = r.w[i];
+}
+template <class Op>
+__device__ __forceinline__ void store2(const Rows2 &r, int64_t i, const Part2 &p)
+{
+    if (Op::WRITE_X) {
+        r.x[0][i] = p.x[0];
+        r.x[1][i] = p.x[1];
+    }
+    if (Op::WRITE_V) {
+        r.v[0][i] = p.v[0];
+        r.v[1][i] = p.v[1];
+        r.v[2][i] = p.v[2];
+    }
+}
+
+template <class Op>
+__global__ void __launch_bounds__(kThreads2) k2_pass(const __grid_constant__ P2<Op> P)
+{
+    extern __shared__ double smem[];
+    constexpr int SLOTS = Tile<Op::D>::SLOTS, W = Tile<Op::D>::W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *wtile = smem + (size_t)warp * SLOTS * 32;
+    double *tile = wtile + lane;
+    const int64_t n_chunks = (P.n + P.chunk - 1) / P.chunk;
+    for (int64_t ch = (int64_t)blockIdx.x * kWarps2 + warp; ch < n_chunks; ch += (int64_t)gridDim.x * kWarps2) {
+        const int64_t lo = ch * P.chunk, hi = min(P.n, lo + P.chunk);
+        int bx = 0, by = 0;
+        if (Op::DEPOSIT) {
+            double t;
+            locate2<0>(P.r.x[0][lo], P.m, bx, t);
+            locate2<1>(P.r.x[1][lo], P.m, by, t);
+            bx = wrapi(bx, P.m.n[0]);
+            by = wrapi(by, P.m.n[1]);
+            for (int s = 0; s < SLOTS; ++s) tile[s * 32] = 0.0;
+        }
+        int64_t i = lo + lane;
+        Part2 a, b;
+        bool ha = i < hi, hb = i + 32 < hi;
+        if (ha) load2<Op>(P.r, i, a);
+        if (hb) load2<Op>(P.r, i + 32, b);
+        while (ha) {
+            const int64_t ni = i + 64;
+            const bool hc = ni < hi, hd = ni + 32 < hi;
+            Part2 c, d;
+            if (hc) load2<Op>(P.r, ni, c);
+            if (hd) load2<Op>(P.r, ni + 32, d);
+            Op::apply(a, P, tile, bx, by);
+            store2<Op>(P.r, i, a);
+            if (hb) {
+                Op::apply(b, P, tile, bx, by);
+                store2<Op>(P.r, i + 32, b);
+            }
+            a = c; b = d;
+            ha = hc; hb = hd;
+            i = ni;
+        }
+        if (Op::DEPOSIT) {
+            __syncwarp();
+            // sum the 32 lane copies of every slot (rotated: conflict free) and add to the global grid
+            const int ox = bx - kR2 - Op::D, oy = by - kR2 - Op::D;
+            for (int s = lane; s < SLOTS; s += 32) {
+                double sum = 0.0;
+#pragma unroll 8
+                for (int l = 0; l < 32; ++l) sum += wtile[(size_t)s * 32 + ((l + lane) & 31)];
+                if (sum != 0.0) {
+                    const int ly = s / W, lx = s - ly * W;
+                    atomicAdd(P.grid + wrapi(ox + lx, P.m.n[0]) + (size_t)wrapi(oy + ly, P.m.n[1]) * P.m.n[0], sum);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// sum_p w v.v, sum_p w v_k: one block-reduced partial per block, finished by k_reduce_partials
+__global__ void __launch_bounds__(256) k2_moments(Rows2 r, int64_t n, double *__restrict__ partials)
+{
+    __shared__ double red[4][256];
+    double s[4] = {0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double w = r.w[i], v1 = r.v[0][i], v2 = r.v[1][i], v3 = r.v[2][i];
+        s[0] += w * (v1 * v1 + v2 * v2 + v3 * v3);
+        s[1] += w * v1;
+        s[2] += w * v2;
+        s[3] += w * v3;
+    }
+    for (int k = 0; k < 4; ++k) red[k][threadIdx.x] = s[k];
+    __syncthreads();
+    for (int h = 128; h > 0; h >>= 1) {
+        if (threadIdx.x < h)
+            for (int k = 0; k < 4; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + h];
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) partials[(size_t)blockIdx.x * 4 + threadIdx.x] = red[threadIdx.x][0];
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static Mesh2 mesh2(const Maxwell2D &mx)
+{
+    Mesh2 m;
+    m.xmin[0] = mx.xmin; m.xmin[1] = mx.ymin;
+    m.d[0] = mx.dx; m.d[1] = mx.dy;
+    m.inv_d[0] = 1.0 / mx.dx; m.inv_d[1] = 1.0 / mx.dy;
+    m.L[0] = mx.Lx; m.L[1] = mx.Ly;
+    m.xmax[0] = mx.xmin + mx.Lx; m.xmax[1] = mx.ymin + mx.Ly;
+    m.n[0] = mx.nx; m.n[1] = mx.ny;
+    return m;
+}
+
+static Rows2 rows2(ParticleGroup &pg)
+{
+    Rows2 r;
+    r.x[0] = pg.row(0); r.x[1] = pg.row(1);
+    r.v[0] = pg.row(2); r.v[1] = pg.row(3); r.v[2] = pg.row(4);
+    r.w = pg.row(5);
+    return r;
+}
+
+template <class Op>
+static void launch2(Splitting2D &h, P2<Op> P, const char *tag)
+{
+    Context &c = ctx();
+    P.r = rows2(*h.pg);
+    P.n = h.pg->n;
+    P.m = mesh2(*h.maxwell);
+    if (P.n <= 0) return;
+    const size_t smem = Op::DEPOSIT ? (size_t)kWarps2 * Tile<Op::D>::SLOTS * 32 * sizeof(double) : 0;
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        GP_CUDA(cudaFuncSetAttribute(k2_pass<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int per_sm = 0;
+    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_pass<Op>, kThreads2, smem));
+    GP_REQUIRE(per_sm >= 1, GEMPIC_EINVAL, "2D pass does not fit on an SM (smem %zu B)", smem);
+    // chunk: a multiple of 64 particles per warp visit, ~16 visits per warp so that the tail stays balanced
+    const int64_t warps = (int64_t)c.sm_count * per_sm * kWarps2;
+    int64_t chunk = (P.n + warps * 16 - 1) / (warps * 16);
+    chunk = std::max<int64_t>(512, std::min<int64_t>((chunk + 63) / 64 * 64, 8192));
+    P.chunk = chunk;
+    const int64_t n_chunks = (P.n + chunk - 1) / chunk;
+    const int grid = (int)std::min<int64_t>((n_chunks + kWarps2 - 1) / kWarps2, (int64_t)c.sm_count * per_sm);
+    if (tag) profile_begin(tag);
+    k2_pass<Op><<<grid, kThreads2, smem, c.stream>>>(P);
+    GP_CUDA(cudaGetLastError());
+    if (tag) profile_end(tag);
+    count_launch();
+}
+
+#define GP_DISPATCH_D0(Dv, ...)                                                           \
+    do {                                                                                  \
+        switch (Dv) {                                                                     \
+        case 1: { constexpr int D0 = 1; __VA_ARGS__; } break;                             \
+        case 2: { constexpr int D0 = 2; __VA_ARGS__; } break;                             \
+        case 3: { constexpr int D0 = 3; __VA_ARGS__; } break;                             \
+        default: ::gempic::fail(GEMPIC_EINVAL, "unsupported spline degree %d", (Dv));      \
+        }                                                                                 \
+    } while (0)
+
+static void zero_grid(double *g, size_t n) { GP_CUDA(cudaMemsetAsync(g, 0, n * sizeof(double), ctx().stream)); }
+
+void hs2d_charge(Splitting2D &h, double *rho_dev)
+{
+    zero_grid(rho_dev, h.nd);
+    GP_DISPATCH_D0(h.maxwell->s_deg_0, {
+        P2<Op2Charge<D0>> P{};
+        P.grid = rho_dev;
+        P.op.wscale = h.pg->charge * h.pg->common_weight;
+        launch2(h, P, "add_charge2d");
+    });
+    allreduce_sum(rho_dev, h.nd);
+}
+
+static void op2_HE(Splitting2D &h, double dt)
+{
+    GP_DISPATCH_D0(h.maxwell->s_deg_0, {
+        P2<Op2HE<D0>> P{};
+        P.f[0] = h.e(0); P.f[1] = h.e(1); P.f[2] = h.e(2);
+        P.op.dtqm = dt * h.pg->q_over_m;
+        launch2(h, P, "operatorHE{2,3}");
+    });
+    double *b[3] = {h.b(0), h.b(1), h.b(2)};
+    const double *e[3] = {h.e(0), h.e(1), h.e(2)};
+    m2d_b_from_e(*h.maxwell, b, dt, e);
+}
+
+static void op2_HB(Splitting2D &h, double dt)
+{
+    double *e[3] = {h.e(0), h.e(1), h.e(2)};
+    const double *b[3] = {h.b(0), h.b(1), h.b(2)};
+    m2d_e_from_b(*h.maxwell, e, dt, b);
+}
+
+static void op2_Hp3(Splitting2D &h, double dt)
+{
+    zero_grid(h.j(2), h.nd);
+    GP_DISPATCH_D0(h.maxwell->s_deg_0, {
+        P2<Op2Hp3<D0>> P{};
+        P.f[0] = h.b(0); P.f[1] = h.b(1);
+        P.grid = h.j(2);
+        P.op.dtqm = dt * h.pg->q_over_m;
+        P.op.wscale_dt = h.pg->charge * h.pg->common_weight * dt;
+        launch2(h, P, "operatorHp3{2,3}");
+    });
+    allreduce_sum(h.j(2), h.nd);
+    m2d_e_from_j(*h.maxwell, h.e(2), h.j(2), 3);
+}
+
+template <int DIR>
+static void op2_Hp12(Splitting2D &h, double dt)
+{
+    zero_grid(h.j(DIR), h.nd);
+    const double hd = DIR == 0 ? h.maxwell->dx : h.maxwell->dy;
+    GP_DISPATCH_D0(h.maxwell->s_deg_0, {
+        P2<Op2Hp12<D0, DIR>> P{};
+        P.f[0] = h.b(2);
+        P.f[1] = DIR == 0 ? h.b(1) : h.b(0);
+        P.grid = h.j(DIR);
+        P.op.dt = dt;
+        P.op.qm_h = h.pg->q_over_m * hd;
+        P.op.wscale_h = h.pg->charge * h.pg->common_weight * hd;
+        launch2(h, P, DIR == 0 ? "operatorHp1{2,3}" : "operatorHp2{2,3}");
+    });
+    allreduce_sum(h.j(DIR), h.nd);
+    m2d_e_from_j(*h.maxwell, h.e(DIR), h.j(DIR), DIR + 1);
+}
+
+void hs2d_operator(Splitting2D &h, int op, double dt)
+{
+    switch (op) {
+    case GEMPIC_OP_HP1: op2_Hp12<0>(h, dt); break;
+    case GEMPIC_OP_HP2: op2_Hp12<1>(h, dt); break;
+    case GEMPIC_OP_HP3: op2_Hp3(h, dt); break;
+    case GEMPIC_OP_HE: op2_HE(h, dt); break;
+    case GEMPIC_OP_HB: op2_HB(h, dt); break;
+    default: fail(GEMPIC_EINVAL, "unknown operator %d", op);
+    }
+}
+
+void hs2d_strang(Splitting2D &h, double dt, int64_t steps)
+{
+    for (int64_t s = 0; s < steps; ++s) {
+        if (h.sort_interval > 0 && h.steps_done % h.sort_interval == 0) pg_sort_2d(*h.pg, *h.maxwell);
+        hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);
+        hs2d_operator(h, GEMPIC_OP_HE, 0.5 * dt);
+        hs2d_operator(h, GEMPIC_OP_HP3, 0.5 * dt);
+        hs2d_operator(h, GEMPIC_OP_HP2, 0.5 * dt);
+        hs2d_operator(h, GEMPIC_OP_HP1, dt);
+        hs2d_operator(h, GEMPIC_OP_HP2, 0.5 * dt);
+        hs2d_operator(h, GEMPIC_OP_HP3, 0.5 * dt);
+        hs2d_operator(h, GEMPIC_OP_HE, 0.5 * dt);
+        hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);
+        h.steps_done++;
+    }
+}
+
+void hs2d_moments(Splitting2D &h, double *out4_dev)
+{
+    Context &c = ctx();
+    const int grid = c.sm_count * 4;
+    double *part = h.scratch.ensure((size_t)grid * 4);
+    k2_moments<<<grid, 256, 0, c.stream>>>(rows2(*h.pg), h.pg->n, part);
+    GP_CUDA(cudaGetLastError());
+    k_reduce_partials<<<1, 128, 0, c.stream>>>(part, grid, 4, out4_dev);
+    GP_CUDA(cudaGetLastError());
+    count_launch(2);
+    allreduce_sum(out4_dev, 4);
+}
+
+}  // namespace gempic
+
+// =============================== C ABI ==========================================================
+using namespace gempic;
+
+extern "C" {
+
+int gempic_hs2d_create(gempic_handle maxwell2d, gempic_handle pgh, gempic_handle *out)
+{
+    GP_API_BEGIN
+    require_init();
+    GP_REQUIRE(out, GEMPIC_EINVAL, "null output handle");
+    auto h = std::make_unique<Splitting2D>();
+    h->maxwell = get<Maxwell2D>(maxwell2d, "TwoDMaxwell");
+    h->pg = get<ParticleGroup>(pgh, "ParticleGroup");
+    GP_REQUIRE(h->pg->D == 2 && h->pg->V == 3, GEMPIC_EASSERT, "dims == (2, 3) (hamiltonian_splitting.jl:47)");
+    GP_REQUIRE(h->pg->W >= 1, GEMPIC_EASSERT, "particle group needs a weight row");
+    GP_REQUIRE(h->maxwell->s_deg_0 >= 1, GEMPIC_EINVAL, "degree");
+    GP_REQUIRE(h->maxwell->nx >= 2 * kR2 + 2 && h->maxwell->ny >= 2 * kR2 + 2, GEMPIC_EINVAL,
+               "HamiltonianSplitting{2,3} needs at least %d cells per direction", 2 * kR2 + 2);
+    h->nd = (size_t)h->maxwell->nx * h->maxwell->ny;
+    h->fields.alloc(10 * h->nd + 16);
+    h->fields.zero(ctx().stream);
+    *out = register_object(std::move(h));
+    GP_API_END
+}
+
+int gempic_hs2d_destroy(gempic_handle hs)
+{
+    GP_API_BEGIN
+    destroy(hs, Kind::Splitting2D, "HamiltonianSplitting{2,3}");
+    GP_API_END
+}
+
+int gempic_hs2d_set_fields(gempic_handle hs, const double *e1, const double *e2, const double *e3, const double *b1,
+                           const double *b2, const double *b3)
+{
+    GP_API_BEGIN
+    require_init();
+    Splitting2D *h = get<Splitting2D>(hs, "HamiltonianSplitting{2,3}");
+    const double *src[6] = {e1, e2, e3, b1, b2, b3};
+    for (int k = 0; k < 6; ++k) {
+        GP_REQUIRE(src[k], GEMPIC_EINVAL, "null field buffer");
+        GP_CUDA(cudaMemcpyAsync(h->fields.p + k * h->nd, src[k], h->nd * sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
+    }
+    GP_CUDA(cudaStreamSynchronize(ctx().stream));
+    GP_API_END
+}
+
+/* any pointer may be NULL (skipped); j1, j2, j3 are the currents of the last Hp1, Hp2, Hp3 */
+int gempic_hs2d_get_fields(gempic_handle hs, double *e1, double *e2, double *e3, double *b1, double *b2, double *b3,
+                           double *j1, double *j2, double *j3)
+{
+    GP_API_BEGIN
+    require_init();
+    Splitting2D *h = get<Splitting2D>(hs, "HamiltonianSplitting{2,3}");
+    double *dst[9] = {e1, e2, e3, b1, b2, b3, j1, j2, j3};
+    for (int k = 0; k < 9; ++k)
+        if (dst[k])
+            GP_CUDA(cudaMemcpyAsync(dst[k], h->fields.p + k * h->nd, h->nd * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+    GP_CUDA(cudaStreamSynchronize(ctx().stream));
+    GP_API_END
+}
+
+int gempic_hs2d_operator(gempic_handle hs, int op, double dt)
+{
+    GP_API_BEGIN
+    require_init();
+    hs2d_operator(*get<Splitting2D>(hs, "HamiltonianSplitting{2,3}"), op, dt);
+    GP_API_END
+}
+
+int gempic_hs2d_strang_splitting(gempic_handle hs, double dt, int64_t number_steps)
+{
+    GP_API_BEGIN
+    require_init();
+    hs2d_strang(*get<Splitting2D>(hs, "HamiltonianSplitting{2,3}"), dt, number_steps);
+    GP_API_END
+}
+
+/* drop-in form with HOST field buffers (the aliased e_dofs / b_dofs of the reference struct):
+ * H2D(e, b) -> number_steps Strang steps -> D2H(e, b), synchronous */
+int gempic_hs2d_strang_splitting_host(gempic_handle hs, double dt, int64_t number_steps, double *e1, double *e2, double *e3,
+                                      double *b1, double *b2, double *b3)
+{
+    int rc = gempic_hs2d_set_fields(hs, e1, e2, e3, b1, b2, b3);
+    if (rc) return rc;
+    rc = gempic_hs2d_strang_splitting(hs, dt, number_steps);
+    if (rc) return rc;
+    return gempic_hs2d_get_fields(hs, e1, e2, e3, b1, b2, b3, nullptr, nullptr, nullptr);
+}
+
+int gempic_hs2d_operator_host(gempic_handle hs, int op, double dt, double *e1, double *e2, double *e3, double *b1,
+                              double *b2, double *b3)
+{
+    int rc = gempic_hs2d_set_fields(hs, e1, e2, e3, b1, b2, b3);
+    if (rc) return rc;
+    rc = gempic_hs2d_operator(hs, op, dt);
+    if (rc) return rc;
+    return gempic_hs2d_get_fields(hs, e1, e2, e3, b1, b2, b3, nullptr, nullptr, nullptr);
+}
+
+/* cell-sort the particles every `interval` Strang steps (0: never; default 1) */
+int gempic_hs2d_set_sort_interval(gempic_handle hs, int interval)
+{
+    GP_API_BEGIN
+    Splitting2D *h = get<Splitting2D>(hs, "HamiltonianSplitting{2,3}");
+    GP_REQUIRE(interval >= 0, GEMPIC_EINVAL, "interval");
+    h->sort_interval = interval;
+    GP_API_END
+}
+
+/* rho[nx*ny] = add_charge! of all particles (degree p x p, get_charge weights), all-reduced over ranks */
+int gempic_hs2d_charge_density(gempic_handle hs, double *rho)
+{
+    GP_API_BEGIN
+    require_init();
+    Splitting2D *h = get<Splitting2D>(hs, "HamiltonianSplitting{2,3}");
+    GP_REQUIRE(rho, GEMPIC_EINVAL, "null buffer");
+    double *dr = h->fields.p + 9 * h->nd;
+    hs2d_charge(*h, dr);
+    d2h(rho, dr, h->nd);
+    GP_API_END
+}
+
+/* out[4] = sum_p w |v|^2, sum_p w v1, sum_p w v2, sum_p w v3 (all ranks) */
+int gempic_hs2d_moments(gempic_handle hs, double *out4)
+{
+    GP_API_BEGIN
+    require_init();
+    Splitting2D *h = get<Splitting2D>(hs, "HamiltonianSplitting{2,3}");
+    GP_REQUIRE(out4, GEMPIC_EINVAL, "null buffer");
+    double *d = h->fields.p + 10 * h->nd;
+    hs2d_moments(*h, d);
+    d2h(out4, d, 4);
+    GP_API_END
+}
+
+int gempic_pg_sort2d(gempic_handle pgh, gempic_handle maxwell2d)
+{
+    GP_API_BEGIN
+    require_init();
+    ParticleGroup *pg = get<ParticleGroup>(pgh, "ParticleGroup");
+    GP_REQUIRE(pg->D == 2, GEMPIC_EINVAL, "2D cell sort needs a D = 2 particle group");
+    pg_sort_2d(*pg, *get<Maxwell2D>(maxwell2d, "TwoDMaxwell"));
+    GP_API_END
+}
+
+}  // extern "C"

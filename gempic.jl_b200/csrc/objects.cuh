@@ -15,6 +15,7 @@ struct ParticleGroup : Object {
     DevBuf<double> data;  // (D+V+W) rows of `stride` doubles
     size_t stride = 0;    // row pitch in doubles (multiple of 32 -> 256 B aligned rows)
     DevBuf<double> sort_tmp;
+    DevBuf<int> sort_keys;    // per-cell counters / cursors of the 2D sort
     uint64_t generation = 0;  // bumped whenever the row pointers change (sort) -> stale graphs
     ParticleGroup() : Object(kKind) {}
     int rows() const { return D + V + W; }
@@ -158,6 +159,25 @@ struct Boris : Object {
     double *acc() { return fields.p + 8 * (size_t)n; }
     Mesh1D mesh() const { return ks0->mesh(maxwell->Lx); }
 };
+
+// HamiltonianSplitting{2,3} on TwoDMaxwell (hs2d.cu)
+struct Splitting2D : Object {
+    static constexpr Kind kKind = Kind::Splitting2D;
+    Maxwell2D *maxwell;
+    ParticleGroup *pg;
+    size_t nd = 0;             // nx * ny
+    DevBuf<double> fields;     // e1 e2 e3 b1 b2 b3 j1 j2 j3 rho (10 * nd) + 16 scalars
+    PartialScratch scratch;
+    int sort_interval = 1;     // cell-sort every k Strang steps (0: never)
+    int64_t steps_done = 0;
+    Splitting2D() : Object(kKind) {}
+    double *e(int c) { return fields.p + (size_t)c * nd; }
+    double *b(int c) { return fields.p + (size_t)(3 + c) * nd; }
+    double *j(int c) { return fields.p + (size_t)(6 + c) * nd; }
+};
+void hs2d_operator(Splitting2D &h, int op, double dt);
+void hs2d_strang(Splitting2D &h, double dt, int64_t steps);
+void pg_sort_2d(ParticleGroup &pg, const Maxwell2D &m);
 
 // operator implementations (hs1d.cu / boris.cu)
 void hs_operator(Splitting &h, int op, double dt, bool inside_strang);

@@ -208,6 +208,87 @@ void pg_sort_1d(ParticleGroup &pg, const Pmc1D &p)
     pg.generation++;
 }
 
+// ---- 2D cell sort (ParticleGroup{2,V}) ------------------------------------------------------------
+// key = cx + cy*nx on the TwoDMaxwell mesh.  Global histogram -> exclusive scan -> scatter with one
+// warp-aggregated cursor reservation per (32 particles, distinct cell).  The order inside a cell depends
+// on the reservation order (only the fp64 summation order of later deposits changes with it).
+struct SortMesh2 {
+    double xmin[2], inv_d[2];
+    int n[2];
+};
+__device__ __forceinline__ int sort_cell2(double x, double y, const SortMesh2 &m)
+{
+    int cx = __double2int_rd((x - m.xmin[0]) * m.inv_d[0]), cy = __double2int_rd((y - m.xmin[1]) * m.inv_d[1]);
+    cx = min(max(cx, 0), m.n[0] - 1);   // positions are kept inside the box; clamp the rounding edge
+    cy = min(max(cy, 0), m.n[1] - 1);
+    return cx + cy * m.n[0];
+}
+__global__ void k_sort2_hist(const double *__restrict__ x, const double *__restrict__ y, int64_t n, SortMesh2 m,
+                             int *__restrict__ hist)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t T = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += T) {
+        const int64_t i = base + lane;
+        const bool active = i < n;
+        const unsigned amask = __ballot_sync(0xffffffffu, active);
+        if (active) {
+            const int cell = sort_cell2(x[i], y[i], m);
+            const unsigned peers = __match_any_sync(amask, cell);
+            if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&hist[cell], __popc(peers));
+        }
+    }
+}
+__global__ void k_sort2_scatter(const double *__restrict__ src, double *__restrict__ dst, size_t stride, int rows, int64_t n,
+                                SortMesh2 m, int *__restrict__ cursor)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t T = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += T) {
+        const int64_t i = base + lane;
+        const bool active = i < n;
+        const unsigned amask = __ballot_sync(0xffffffffu, active);
+        if (active) {
+            const int cell = sort_cell2(src[i], src[stride + i], m);
+            const unsigned peers = __match_any_sync(amask, cell);
+            const int leader = __ffs(peers) - 1;
+            int start = 0;
+            if (lane == leader) start = atomicAdd(&cursor[cell], __popc(peers));
+            start = __shfl_sync(peers, start, leader);
+            const int64_t d = (int64_t)start + __popc(peers & ((1u << lane) - 1u));
+            for (int r = 0; r < rows; ++r) dst[(size_t)r * stride + d] = src[(size_t)r * stride + i];
+        }
+    }
+}
+
+void pg_sort_2d(ParticleGroup &pg, const Maxwell2D &mx)
+{
+    Context &c = ctx();
+    if (pg.n < 2) return;
+    GP_REQUIRE(pg.D == 2, GEMPIC_EINVAL, "2D cell sort needs a D = 2 particle group");
+    GP_REQUIRE(pg.n < (int64_t)2147483647, GEMPIC_EINVAL, "sort supports < 2^31 particles per GPU");
+    SortMesh2 m;
+    m.xmin[0] = mx.xmin; m.xmin[1] = mx.ymin;
+    m.inv_d[0] = 1.0 / mx.dx; m.inv_d[1] = 1.0 / mx.dy;
+    m.n[0] = mx.nx; m.n[1] = mx.ny;
+    const int64_t cells = (int64_t)mx.nx * mx.ny;
+    if (pg.sort_keys.n < (size_t)cells) pg.sort_keys.alloc((size_t)cells);
+    if (pg.sort_tmp.n < pg.data.n) pg.sort_tmp.alloc(pg.data.n);
+    GP_CUDA(cudaMemsetAsync(pg.sort_keys.p, 0, sizeof(int) * cells, c.stream));
+    const int grid = c.sm_count * 8;
+    k_sort2_hist<<<grid, 256, 0, c.stream>>>(pg.row(0), pg.row(1), pg.n, m, pg.sort_keys.p);
+    GP_CUDA(cudaGetLastError());
+    k_sort_scan<<<1, 1024, 0, c.stream>>>(pg.sort_keys.p, cells);
+    GP_CUDA(cudaGetLastError());
+    k_sort2_scatter<<<grid, 256, 0, c.stream>>>(pg.data.p, pg.sort_tmp.p, pg.stride, pg.rows(), pg.n, m, pg.sort_keys.p);
+    GP_CUDA(cudaGetLastError());
+    count_launch(3);
+    GP_CUDA(cudaStreamSynchronize(c.stream));
+    std::swap(pg.data.p, pg.sort_tmp.p);
+    std::swap(pg.data.n, pg.sort_tmp.n);
+    pg.generation++;
+}
+
 // ---- synthetic loads -------------------------------------------------------------------------
 // Counter-based generator: splitmix64 of (seed, global particle index, stream) -> reproducible
 // for any sharding of the index range.  Statistical (not bitwise) counterpart of

@@ -41,7 +41,7 @@ typedef enum {
 /* smoothing_type symbols of ParticleMeshCoupling1D/2D (src/particle_mesh_coupling_1d.jl:56-65) */
 enum { GEMPIC_COLLOCATION = 0, GEMPIC_GALERKIN = 1 };
 /* operators of src/hamiltonian_splitting_1d2v.jl / _1d1v.jl */
-enum { GEMPIC_OP_HP1 = 1, GEMPIC_OP_HP2 = 2, GEMPIC_OP_HE = 3, GEMPIC_OP_HB = 4 };
+enum { GEMPIC_OP_HP1 = 1, GEMPIC_OP_HP2 = 2, GEMPIC_OP_HE = 3, GEMPIC_OP_HB = 4, GEMPIC_OP_HP3 = 5 /* 2d3v only */ };
 /* field selectors for gempic_hs_get_field / gempic_boris_get_field */
 enum {
     GEMPIC_F_E1 = 0, GEMPIC_F_E2 = 1, GEMPIC_F_B = 2, GEMPIC_F_J1 = 3, GEMPIC_F_J2 = 4,
@@ -201,6 +201,34 @@ int gempic_hs_strang_splitting_host(gempic_handle hs, double dt, int64_t number_
 /* Same trajectory with the particle passes of a Strang step fused:
  * fuse = 0 one kernel per reference operator (default), 1 fused [HE,Hp2,Hp1,Hp2] pass. */
 int gempic_hs_set_fusion(gempic_handle hs, int fuse);
+
+/* ---- HamiltonianSplitting{2,3} on TwoDMaxwell (BASELINE config 5) ---------------------------
+ * Fills the empty src/hamiltonian_splitting_2d3v.jl: the 2D extension of the operators of
+ * src/hamiltonian_splitting_1d2v.jl:41-236 and of strang_splitting! (src/hamiltonian_splitting.jl:98-108)
+ * on ParticleGroup{2,3} (rows x1,x2,v1,v2,v3,w); operator order HB HE Hp3 Hp2 Hp1 Hp2 Hp3 HE HB.
+ * Field vectors are flat nx*ny dofs, x fastest: e = (E1,E2,E3) 1-form, b = (B1,B2,B3) 2-form. */
+int gempic_hs2d_create(gempic_handle maxwell2d, gempic_handle pg, gempic_handle *out);
+int gempic_hs2d_destroy(gempic_handle hs);
+int gempic_hs2d_set_fields(gempic_handle hs, const double *e1, const double *e2, const double *e3, const double *b1,
+                           const double *b2, const double *b3);
+/* NULL pointers are skipped; j1,j2,j3 = currents of the last Hp1, Hp2, Hp3 */
+int gempic_hs2d_get_fields(gempic_handle hs, double *e1, double *e2, double *e3, double *b1, double *b2, double *b3,
+                           double *j1, double *j2, double *j3);
+int gempic_hs2d_operator(gempic_handle hs, int op, double dt);                         /* GEMPIC_OP_* */
+int gempic_hs2d_strang_splitting(gempic_handle hs, double dt, int64_t number_steps);
+/* drop-in forms with HOST field buffers (the aliased e_dofs / b_dofs): H2D -> op -> D2H -> sync */
+int gempic_hs2d_operator_host(gempic_handle hs, int op, double dt, double *e1, double *e2, double *e3, double *b1,
+                              double *b2, double *b3);
+int gempic_hs2d_strang_splitting_host(gempic_handle hs, double dt, int64_t number_steps, double *e1, double *e2,
+                                      double *e3, double *b1, double *b2, double *b3);
+/* cell-sort the particles every `interval` Strang steps (0: never; default 1) */
+int gempic_hs2d_set_sort_interval(gempic_handle hs, int interval);
+/* add_charge! of all particles onto the degree p x p dofs (get_charge weights), summed over ranks */
+int gempic_hs2d_charge_density(gempic_handle hs, double *rho);
+/* out[4] = sum_p w |v|^2, sum_p w v1, sum_p w v2, sum_p w v3, summed over ranks (diagnostics.jl:197-211) */
+int gempic_hs2d_moments(gempic_handle hs, double *out4);
+/* periodic cell sort of a ParticleGroup{2,V} on the mesh of a TwoDMaxwell */
+int gempic_pg_sort2d(gempic_handle pg, gempic_handle maxwell2d);
 
 /* ---- HamiltonianSplittingBoris (src/hamiltonian_splitting_boris.jl:23-288) ------------ */
 int gempic_boris_create(gempic_handle maxwell, gempic_handle pmc0, gempic_handle pmc1, gempic_handle pg,

@@ -1,0 +1,156 @@
+"""HamiltonianSplitting{2,3} on the device (csrc/hs2d.cu) against the CPU oracle (oracle/splitting2d3v.py) on
+identical seeded particle sets, plus the invariants of the scheme at a size the oracle cannot reach.
+
+Tolerance: 1e-12 relative for particles and dofs after each operator (fp64; the device integrates the
+splines with primitives, the oracle with the reference's Gauss-Legendre rule -- both exact for the
+polynomial pieces; the RED / tree summation order is the only other difference)."""
+import numpy as np
+import pytest
+
+from oracle import maxwell2d as m2
+from oracle import oracle as orc_mod
+from oracle import splitting2d3v as s2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def rel(a, b):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300)
+
+
+def make_state(n, box, seed, vth=(1.0, 1.0, 0.5)):
+    (xmin, lx), (ymin, ly) = box
+    rng = np.random.default_rng(seed)
+    st = np.empty((6, n))
+    st[0] = xmin + rng.uniform(0, lx, n)
+    st[1] = ymin + rng.uniform(0, ly, n)
+    for k in range(3):
+        st[2 + k] = vth[k] * rng.normal(size=n)
+    st[5] = lx * ly * (1.0 + 0.1 * rng.uniform(size=n))
+    return st
+
+
+def build(gp, n, nx, ny, deg, seed, box=((0.0, 4 * np.pi), (0.0, 4 * np.pi)), resident=False, charge=-1.0, mass=1.0):
+    (xmin, lx), (ymin, ly) = box
+    st = make_state(n, box, seed)
+    rng = np.random.default_rng(seed + 1)
+    nd = nx * ny
+    e0 = [0.1 * rng.normal(size=nd) for _ in range(3)]
+    b0 = [0.1 * rng.normal(size=nd) for _ in range(3)]
+    mesh_o = orc_mod.TwoDGrid(xmin, xmin + lx, nx, ymin, ymin + ly, ny)
+    pg_o = s2.ParticleGroup23(n, charge=charge, mass=mass)
+    pg_o.array[:, :] = st
+    ho = s2.HamiltonianSplitting2D3V(m2.TwoDMaxwell(mesh_o, deg), pg_o, [v.copy() for v in e0], [v.copy() for v in b0])
+    pg_g = gp.ParticleGroup(2, 3, n, charge=charge, mass=mass)
+    pg_g.upload(st)
+    mg = gp.TwoDMaxwell(gp.TwoDGrid(xmin, xmin + lx, nx, ymin, ymin + ly, ny), deg)
+    hg = gp.HamiltonianSplitting2D3V(mg, pg_g, [v.copy() for v in e0], [v.copy() for v in b0], resident=resident)
+    hg.set_sort_interval(0)   # per-particle comparison: keep the particle order
+    return ho, hg
+
+
+def check(ho, hg, box, tol=TOL, what=""):
+    a, b = hg.particle_group.to_host(), ho.particle_group.array
+    for d in range(2):
+        L = box[d][1]
+        dx = np.abs(a[d] - b[d])
+        dx = np.minimum(dx, np.abs(dx - L))
+        assert np.max(dx) / L < tol, f"{what}: x{d + 1}"
+    for k in range(2, 5):
+        assert rel(a[k], b[k]) < tol, f"{what}: v{k - 1}"
+    for c in range(3):
+        assert rel(hg.e_dofs[c], ho.e_dofs[c]) < tol, f"{what}: e{c + 1}"
+        assert rel(hg.b_dofs[c], ho.b_dofs[c]) < tol, f"{what}: b{c + 1}"
+
+
+BOX = ((0.0, 4 * np.pi), (0.0, 4 * np.pi))
+
+
+@pytest.mark.parametrize("n,nx,ny,deg", [(20_000, 16, 16, 3), (9_999, 12, 20, 3), (5_000, 10, 8, 2), (4_000, 8, 8, 1), (1, 16, 16, 3)])
+def test_operators_match_oracle(gp, n, nx, ny, deg):
+    ho, hg = build(gp, n, nx, ny, deg, seed=n)
+    for op, dt in (("operatorHB", 0.025), ("operatorHE", 0.025), ("operatorHp3", 0.025), ("operatorHp2", 0.025),
+                   ("operatorHp1", 0.05), ("operatorHp2", 0.025), ("operatorHp3", 0.025), ("operatorHE", 0.025),
+                   ("operatorHB", 0.025)):
+        getattr(ho, op)(dt)
+        getattr(hg, op)(dt)
+        check(ho, hg, BOX, what=op)
+    jo, jg = ho.j_dofs, hg.j_dofs
+    for c in range(3):
+        assert rel(jg[c], jo[c]) < TOL, f"j{c + 1}"
+    assert rel(hg.charge_density(), ho.charge_density()) < TOL
+
+
+def test_large_displacements_take_the_general_path(gp):
+    """dt*v of several cells and an offset box: the slow path (global REDs, any number of crossings)"""
+    box = ((-2.0, 3.0), (1.0, 2.0))
+    ho, hg = build(gp, 3000, 12, 10, 3, seed=77, box=box)
+    for op, dt in (("operatorHp1", 0.9), ("operatorHp2", 0.7), ("operatorHp1", -0.8), ("operatorHp2", -1.1)):
+        getattr(ho, op)(dt)
+        getattr(hg, op)(dt)
+        check(ho, hg, box, tol=1e-11, what=op)
+
+
+def test_strang_resident_sorted_matches_oracle(gp):
+    """device-resident fields, cell sort every step: particles are permuted, so the sets are compared after
+    ordering both by (x1, x2); fields must agree directly"""
+    n = 30_000
+    ho, hg = build(gp, n, 16, 16, 3, seed=5, resident=True)
+    hg.set_sort_interval(1)
+    ho.strang_splitting(0.05, 3)
+    hg.strang_splitting(0.05, 3)
+    hg.sync_fields()
+    for c in range(3):
+        assert rel(hg.e_dofs[c], ho.e_dofs[c]) < 1e-11
+        assert rel(hg.b_dofs[c], ho.b_dofs[c]) < 1e-11
+    a, b = hg.particle_group.to_host(), ho.particle_group.array
+    ka, kb = np.lexsort((a[1], a[0])), np.lexsort((b[1], b[0]))
+    assert np.max(np.abs(a[:, ka] - b[:, kb])) < 1e-9   # chaotic amplification over 3 steps; order must match
+    # the sort really ordered the particles by cell
+    cell = np.floor(a[0] / (4 * np.pi / 16)).astype(int) + 16 * np.floor(a[1] / (4 * np.pi / 16)).astype(int)
+    hg.particle_group.sort(hg.maxwell_solver)
+    a = hg.particle_group.to_host()
+    cell = np.floor(a[0] / (4 * np.pi / 16)).astype(int) + 16 * np.floor(a[1] / (4 * np.pi / 16)).astype(int)
+    assert np.all(np.diff(cell) >= 0)
+
+
+def test_invariants_at_scale(gp):
+    """2e6 particles on 64x64, degree 3 (the BASELINE config 5 grid): Gauss law conserved to round-off,
+    total charge exact, energy drift O(dt^2)"""
+    n, nx = 2_000_000, 64
+    L = 4 * np.pi
+    pg = gp.ParticleGroup(2, 3, n)
+    pg.sample("landau", 0.0, L, alpha=0.5, k=0.5, sigma=(1.0, 1.0, 1.0), seed=1234)
+    mg = gp.TwoDMaxwell(gp.TwoDGrid(0.0, L, nx, 0.0, L, nx), 3)
+    nd = nx * nx
+    e = [np.zeros(nd) for _ in range(3)]
+    b = [np.zeros(nd) for _ in range(3)]
+    h = gp.HamiltonianSplitting2D3V(mg, pg, e, b, resident=True)
+    rho = h.charge_density()
+    assert abs(rho.sum() - L * L) < 1e-9 * L * L            # sum_p q w / N = Lx Ly
+    mg.compute_e_from_rho(e, rho - rho.mean())               # neutralising background
+    b[2][:] = 1e-3 * np.cos(2 * np.pi * (np.arange(nd) % nx) / nx)
+    h.upload_fields()
+    r0 = h.gauss_residual()
+    en0 = sum(h.energies())
+    h.strang_splitting(0.05, 5)
+    r1 = h.gauss_residual()
+    assert np.max(np.abs(r1 - r0)) < 1e-11 * np.max(np.abs(rho))
+    en1 = sum(h.energies())
+    assert abs(en1 - en0) < 1e-3 * en0
+    st = pg.to_host()
+    assert np.all((st[0] >= 0) & (st[0] < L) & (st[1] >= 0) & (st[1] < L))
+    assert np.all(np.isfinite(st))
+
+
+def test_argument_errors(gp):
+    mg = gp.TwoDMaxwell(gp.TwoDGrid(0.0, 1.0, 16, 0.0, 1.0, 16), 3)
+    nd = 256
+    f = lambda: [np.zeros(nd) for _ in range(3)]
+    with pytest.raises(gp.AssertionFailed):
+        gp.HamiltonianSplitting2D3V(mg, gp.ParticleGroup(1, 2, 8), f(), f())
+    h = gp.HamiltonianSplitting2D3V(mg, gp.ParticleGroup(2, 3, 8), f(), f())
+    with pytest.raises(gp.ArgumentError):
+        h._op(9, 0.1)
