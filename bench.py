@@ -56,6 +56,13 @@ WORKLOADS = {
                        "(BASELINE configs[3])",
                   L=4 * math.pi, sigma=(1.0, 1.0), kind="landau", alpha=0.5, k=0.5, integrator="boris"),
 }
+WORKLOADS["2d3v"] = dict(name="2d3v HamiltonianSplitting with TwoDMaxwell, 64x64 cells, deg 3 splines, Landau load along x1, dt 0.05 "
+                              "(BASELINE configs[4] at one GPU's share: 1.25e8 particles per GPU)",
+                         L=4 * math.pi, sigma=(1.0, 1.0, 1.0), kind="landau", alpha=0.5, k=0.5, integrator="hs2d")
+NX2 = 64
+# 2d3v rows x1,x2,v1,v2,v3,w: HE 40 R + 24 W, Hp3 48 R + 16 W, Hp1/Hp2 48 R + 24 W; sort 2 x 48 + keys
+BYTES2 = {"operatorHE{2,3}": 64, "operatorHp3{2,3}": 64, "operatorHp1{2,3}": 72, "operatorHp2{2,3}": 72, "cell sort 2d": 112,
+          "strang_step": 2 * 64 + 2 * 64 + 3 * 72}
 # algorithmic DRAM bytes per particle of each pass (fp64 SoA rows x, v1, v2, w; SURVEY section 8d / DESIGN.md)
 BYTES = {"operatorHE": 40, "operatorHp2": 40, "operatorHp1": 48, "strang_step": 208,
          "fused[HE,Hp2,Hp1,Hp2]": 56, "fused[HE,HE,Hp2,Hp1,Hp2]": 56, "boris_step": 56, "boris_strang_step": 56}
@@ -193,12 +200,167 @@ def cpu_reference(n_cpu: int, steps: int, warmup: int, threads: int | None = Non
                       f"reference Julia path with OpenMP chunks -- Julia unavailable", "seconds": dt}, dt / steps
 
 
+def cpu_reference_2d(n_cpu: int, steps: int, warmup: int):
+    """the serial C restatement of the 2d3v operators (oracle/splitting2d3v.py) on a bounded sample"""
+    from oracle import maxwell2d as m2
+    from oracle import oracle as orc
+    from oracle import splitting2d3v as s2
+
+    wl = WORKLOADS["2d3v"]
+    L = wl["L"]
+    rng = np.random.default_rng(1234)
+    st1 = host_state(dict(wl, sigma=(1.0, 1.0)), n_cpu, rng)
+    pg = s2.ParticleGroup23(n_cpu)
+    pg.array[0], pg.array[1] = st1[0], rng.uniform(0, L, n_cpu)
+    pg.array[2], pg.array[3], pg.array[4] = st1[1], st1[2], rng.normal(size=n_cpu)
+    pg.array[5] = L * L
+    mx = m2.TwoDMaxwell(orc.TwoDGrid(0.0, L, NX2, 0.0, L, NX2), DEG)
+    nd = NX2 * NX2
+    e, b = [np.zeros(nd) for _ in range(3)], [np.zeros(nd) for _ in range(3)]
+    h = s2.HamiltonianSplitting2D3V(mx, pg, e, b)
+    rho = h.charge_density()
+    mx.compute_e_from_rho(e, rho - rho.mean())
+    for _ in range(warmup):
+        h.strang_splitting(DT, 1)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        h.strang_splitting(DT, 1)
+    dt = time.perf_counter() - t0
+    return {"value": n_cpu * steps / dt, "unit": "particle-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{n_cpu} particles x {steps} Strang steps (same 2d3v config), serial C restatement of the 2D "
+                      f"extension of the reference operators -- the reference has no 2d3v integrator and Julia is unavailable",
+            "seconds": dt}, dt / steps
+
+
+def run_ours_2d(args):
+    import torch
+
+    import __graft_entry__ as ge
+
+    gp = ge.load_package()
+    dc = gp.DistributedContext()
+    if dc.world_size != args.gpus and dc.world_size > 1:
+        args.gpus = dc.world_size
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: libgempic_b200 has no CPU path")
+    dc.init_library_comm()
+    Lib = gp.load()
+    wl = WORKLOADS["2d3v"]
+    L = wl["L"]
+    n_local = args.particles if args.particles != 100_000_000 else 125_000_000
+    n_global = n_local * dc.world_size
+    pg = gp.ParticleGroup(2, 3, n_local, common_weight=1.0 / n_global)
+    pg.sample("landau", 0.0, L, alpha=wl["alpha"], k=wl["k"], sigma=wl["sigma"], seed=1234, first_index=dc.rank * n_local)
+    mx = gp.TwoDMaxwell(gp.TwoDGrid(0.0, L, NX2, 0.0, L, NX2), DEG)
+    nd = NX2 * NX2
+    e, b = [np.zeros(nd) for _ in range(3)], [np.zeros(nd) for _ in range(3)]
+    h = gp.HamiltonianSplitting2D3V(mx, pg, e, b, resident=True)
+    h.set_sort_interval(args.sort_interval)
+    rho = h.charge_density()
+    total_charge = float(rho.sum())
+    mx.compute_e_from_rho(e, rho - rho.mean())
+    b[2][:] = BETA * np.cos(2 * np.pi * (np.arange(nd) % NX2) / NX2)
+    h.upload_fields()
+    r0 = h.gauss_residual()
+    stream = torch.cuda.ExternalStream(gp.stream_ptr(), device=torch.device("cuda", dc.local_rank))
+
+    def timed(fn):
+        dc.barrier(); gp.synchronize(); torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        fn()
+        ev1.record(stream)
+        gp.synchronize(); torch.cuda.synchronize(); dc.barrier()
+        return dc.max_over_ranks(ev0.elapsed_time(ev1))
+
+    h.strang_splitting(DT, args.warmup)
+    gp.synchronize()
+    sampler = ClockSampler(dc.local_rank)
+    if dc.rank == 0:
+        sampler.start()
+    _lib = sys.modules["gempic_jl_b200._lib"]
+    _lib.check(Lib.gempic_profile_enable(C.c_int(1)))
+    gp.launch_count(reset=True)
+    ms = timed(lambda: h.strang_splitting(DT, args.steps))
+    launches = gp.launch_count()
+    prof, slot = {}, 0
+    while True:
+        tag = C.create_string_buffer(64)
+        t, cnt = C.c_double(), C.c_int64()
+        if Lib.gempic_profile_read(C.c_int(slot), tag, C.c_int(64), C.byref(t), C.byref(cnt)) != 0:
+            break
+        prof[tag.value.decode()] = (t.value, cnt.value)
+        slot += 1
+    _lib.check(Lib.gempic_profile_enable(C.c_int(0)))
+    clocks = sampler.stop() if dc.rank == 0 else None
+    value = n_global * args.steps / (ms * 1e-3)
+
+    # e2e: host field buffers every step (6 x nx*ny doubles in, 6 out), synchronous
+    h.sync_fields()
+    h_host = gp.HamiltonianSplitting2D3V(mx, pg, e, b, resident=False)
+    h_host.set_sort_interval(args.sort_interval)
+    for _ in range(2):
+        h_host.strang_splitting(DT, 1)
+    dc.barrier(); gp.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h_host.strang_splitting(DT, 1)
+    gp.synchronize()
+    e2e_s = dc.max_over_ranks(time.perf_counter() - t0)
+
+    # sanity: the timed state is a real simulation (charge exact, Gauss law conserved, finite fields)
+    h.upload_fields()
+    r1 = h.gauss_residual()
+    assert abs(total_charge - L * L) < 1e-9 * L * L, "total charge is wrong"
+    assert np.max(np.abs(r1 - r0)) < 1e-10 * np.max(np.abs(rho)), "discrete Gauss law violated -- the step did not do its work"
+    assert all(np.all(np.isfinite(v)) for v in e + b)
+
+    if dc.rank == 0:
+        peak, peak_src = peaks()
+        passes = {k: v for k, v in prof.items() if k in BYTES2 and k != "cell sort 2d"}
+        dom = max(passes, key=lambda k: passes[k][0]) if passes else None
+        roof = None
+        if dom:
+            t_ms = prof[dom][0] / prof[dom][1]
+            achieved = BYTES2[dom] * n_local / (t_ms * 1e-3) / 1e9
+            tr = ncu_traffic(dom)
+            roof = {"bound": "hbm", "kernel": f"k2_pass<{dom}>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": (tr["dram_bytes_per_particle"] * n_local if tr else None),
+                    "traffic_note": (f"{tr['dram_bytes_per_particle']} B/particle, {tr['source']}" if tr else None),
+                    "peak_source": peak_src, "algorithmic_bytes_per_particle": BYTES2[dom], "avg_launch_ms": t_ms,
+                    "all_passes": {k: {"avg_ms": v[0] / max(v[1], 1), "launches": v[1],
+                                       "GBps": BYTES2.get(k, 0) * n_local / (v[0] / max(v[1], 1) * 1e-3) / 1e9 if v[1] else None}
+                                   for k, v in prof.items()},
+                    "step_GBps_vs_unfused_bytes": BYTES2["strang_step"] * n_local / (ms / args.steps * 1e-3) / 1e9}
+        cpu = None
+        if args.gpus == 1 and not args.no_cpu:
+            cpu, _ = cpu_reference_2d(min(args.cpu_particles, 400_000), 2, 1)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cfg = {"workload": wl["name"], "particles_per_gpu": int(n_local), "n_cells": [NX2, NX2], "spline_degree": [DEG, DEG - 1],
+               "dt": DT, "parallelism": f"particles sharded over {dc.world_size} GPU(s), NCCL allreduce of j1/j2/j3",
+               "l2_policy": "inputs (48 B/particle x N >> 126 MB L2) stream from HBM every pass; no flush needed",
+               "kernels": f"one pass per operator (HE, Hp3, Hp2, Hp1, Hp2, Hp3, HE), cell sort every {args.sort_interval} step(s)"}
+        emit({"metric": "particle-steps/s per Strang step", "value": value, "unit": "particle-steps/s", "n_gpus": dc.world_size,
+              "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+              "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+              "e2e": {"value": n_global * args.steps / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 6 * nd * 8,
+                      "d2h_bytes_per_step": 6 * nd * 8, "steps": args.steps,
+                      "what": "gempic_hs2d_strang_splitting_host: host e[3], b[3] in and out, synchronous"},
+              "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu})
+    dc.finalize()
+    return 0
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     n_cpu = args.cpu_particles
-    base, sec_per_step = cpu_reference(n_cpu, args.steps, args.warmup, workload=args.workload)
+    if args.workload == "2d3v":
+        n_cpu = min(n_cpu, 400_000)
+        base, sec_per_step = cpu_reference_2d(n_cpu, args.steps, args.warmup)
+    else:
+        base, sec_per_step = cpu_reference(n_cpu, args.steps, args.warmup, workload=args.workload)
     line = {
         "impl": "reference", "metric": "particle-steps/s per Strang step", "value": base["value"], "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3,
@@ -412,11 +574,14 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="weibel", choices=sorted(WORKLOADS), help="weibel = BASELINE configs[1] (the metric's config)")
+    ap.add_argument("--sort-interval", type=int, default=1, help="2d3v: cell sort every k Strang steps")
     ap.add_argument("--fuse", type=int, default=1, help="1: fused particle passes (default), 0: one kernel per reference operator")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3   # timing rule: W >= 3
-    return run_reference(args) if args.impl == "reference" else run_ours(args)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours_2d(args) if args.workload == "2d3v" else run_ours(args)
 
 
 if __name__ == "__main__":

@@ -18,12 +18,13 @@
 // Kernel design (k2_pass).  A 64x64 grid is 32 KB per component: it cannot be privatised per lane like
 // the 1D grids.  Particles are kept cell-sorted (pg_sort_2d) and every warp streams a contiguous chunk
 // of them, so the dofs it touches lie in a small window around the cell of the chunk's first particle:
-//   * deposits go to a LANE-PRIVATE window tile in shared memory ((2R+1+p)^2 dofs, R = 3 cells of drift
+//   * deposits go to a LANE-PRIVATE window tile in shared memory ((2R+1+p)^2 dofs, R = 2 cells of drift
 //     tolerance; slot s of lane l at (s*32 + l)*8 B): plain LDS/DADD/STS, no atomics, conflict free.  At
 //     the end of the chunk the 32 copies are summed and added to the global grid with one fp64 RED per
-//     dof.  Particles outside the window (never, while the sort is fresh) fall back to global REDs;
-//   * gathers read the field dofs straight from global memory: the lanes of a warp share (nearly) the
-//     same stencil, so every load is a broadcast hit in L1;
+//     dof.  Particles outside the window (rare while the sort is fresh) fall back to global REDs;
+//   * the field dofs of the same window are staged once per chunk in a small warp-shared tile, so a gather
+//     is a run of LDS with compile-time offsets from one base (the lanes of a warp share (nearly) the
+//     same stencil: broadcast, conflict free); outside the window a particle reads global memory;
 //   * the next two particles of every lane are loaded before the current two are processed.
 #include <algorithm>
 
@@ -32,8 +33,8 @@
 
 namespace gempic {
 
-constexpr int kR2 = 3;          // window radius (cells) around the chunk's base cell
-constexpr int kWarps2 = 8;      // warps per block
+constexpr int kR2 = 2;          // window radius (cells) around the chunk's base cell
+constexpr int kWarps2 = 4;      // warps per block
 constexpr int kThreads2 = kWarps2 * 32;
 
 struct Mesh2 {
@@ -123,105 +124,187 @@ struct P2 {
     typename Op::Params op;
 };
 
+// Window of a warp: cells base-R .. base+R in both directions; dofs base-R-D0 .. base+R, i.e. W x W with
+//   local dof index = (cell - base) + R + (D0 - degree) + k,  k = 0..degree.
 template <int D0>
 struct Tile {
     static constexpr int W = 2 * kR2 + 1 + D0;
     static constexpr int SLOTS = W * W;
 };
 
-// ---- operatorHE: v += dt q/m E(x) -------------------------------------------------------------
+// sum_{b<=DY} (sum_{a<=DX} q[b*W + a] bx[a]) by[b] on a shared field tile (q = first dof of the stencil)
+template <int DX, int DY, int W>
+__device__ __forceinline__ double eval_tile(const double *__restrict__ q, const double (&bx)[DX + 1], const double (&by)[DY + 1])
+{
+    double v = 0.0;
+#pragma unroll
+    for (int b = 0; b <= DY; ++b) {
+        double s = q[b * W] * bx[0];
+#pragma unroll
+        for (int a = 1; a <= DX; ++a) s = fma(q[b * W + a], bx[a], s);
+        v = fma(s, by[b], v);
+    }
+    return v;
+}
+
+struct V3 { double v0, v1, v2; };
+
+// ---- operatorHE: v += dt q/m E(x).  fields: E1 (D1,D0), E2 (D0,D1), E3 (D0,D0) ------------------------
 template <int D0>
 struct Op2HE {
     static constexpr bool DEPOSIT = false, WRITE_X = false, WRITE_V = true;
-    static constexpr int D = D0;
+    static constexpr int D = D0, NF = 3;
     struct Params { double dtqm; };
-    static __device__ __forceinline__ void apply(Part2 &p, const P2<Op2HE> &P, double *, int, int)
+    using PP = P2<Op2HE>;
+
+    static __device__ __noinline__ V3 slow(double x, double y, const PP &P)
     {
         constexpr int D1 = D0 - 1;
         int cx, cy, ix[D0 + 1], iy[D0 + 1];
         double tx, ty, bx0[D0 + 1], bx1[D1 + 1], by0[D0 + 1], by1[D1 + 1];
-        locate2<0>(p.x[0], P.m, cx, tx);
-        locate2<1>(p.x[1], P.m, cy, ty);
+        locate2<0>(x, P.m, cx, tx);
+        locate2<1>(y, P.m, cy, ty);
         stencil<D0>(cx, P.m.n[0], ix);
         stencil<D0>(cy, P.m.n[1], iy);
         basis_pp<D0>(tx, bx0); basis_pp<D1>(tx, bx1);
         basis_pp<D0>(ty, by0); basis_pp<D1>(ty, by1);
         const int nx = P.m.n[0];
-        p.v[0] = fma(P.op.dtqm, eval2<D1, D0, 1, 0, D0>(P.f[0], nx, ix, iy, bx1, by0), p.v[0]);
-        p.v[1] = fma(P.op.dtqm, eval2<D0, D1, 0, 1, D0>(P.f[1], nx, ix, iy, bx0, by1), p.v[1]);
-        p.v[2] = fma(P.op.dtqm, eval2<D0, D0, 0, 0, D0>(P.f[2], nx, ix, iy, bx0, by0), p.v[2]);
+        return V3{eval2<D1, D0, 1, 0, D0>(P.f[0], nx, ix, iy, bx1, by0), eval2<D0, D1, 0, 1, D0>(P.f[1], nx, ix, iy, bx0, by1),
+                  eval2<D0, D0, 0, 0, D0>(P.f[2], nx, ix, iy, bx0, by0)};
+    }
+
+    static __device__ __forceinline__ void apply(Part2 &p, const PP &P, const double *ft, double *, int bx, int by)
+    {
+        constexpr int D1 = D0 - 1, W = Tile<D0>::W, WW = W * W;
+        int cx, cy;
+        double tx, ty;
+        locate2<0>(p.x[0], P.m, cx, tx);
+        locate2<1>(p.x[1], P.m, cy, ty);
+        const int rx = rel_cell(cx, bx, P.m.n[0]), ry = rel_cell(cy, by, P.m.n[1]);
+        V3 e;
+        if (__builtin_expect(rx >= -kR2 && rx <= kR2 && ry >= -kR2 && ry <= kR2, 1)) {
+            double bx0[D0 + 1], bx1[D1 + 1], by0[D0 + 1], by1[D1 + 1];
+            basis_pp<D0>(tx, bx0); basis_pp<D1>(tx, bx1);
+            basis_pp<D0>(ty, by0); basis_pp<D1>(ty, by1);
+            const double *q = ft + (ry + kR2) * W + rx + kR2;
+            e.v0 = eval_tile<D1, D0, W>(q + 1, bx1, by0);
+            e.v1 = eval_tile<D0, D1, W>(q + WW + W, bx0, by1);
+            e.v2 = eval_tile<D0, D0, W>(q + 2 * WW, bx0, by0);
+        } else {
+            e = slow(p.x[0], p.x[1], P);
+        }
+        p.v[0] = fma(P.op.dtqm, e.v0, p.v[0]);
+        p.v[1] = fma(P.op.dtqm, e.v1, p.v[1]);
+        p.v[2] = fma(P.op.dtqm, e.v2, p.v[2]);
     }
 };
 
-// (D0+1)^2 deposit of wv * bx0 (x) by0 at cell (cx, cy): lane-private tile or global fallback
+// (D0+1)^2 deposit of wv * wx (x) wy into the lane-private tile at local dof (lx, ly)
 template <int D0>
-__device__ __forceinline__ void deposit_pp(double *tile, double *__restrict__ grid, const Mesh2 &m, int cx, int cy, int bx, int by,
-                                           const double (&wx)[D0 + 1], const double (&wy)[D0 + 1], double wv)
+__device__ __forceinline__ void deposit_tile(double *tile, int lx, int ly, const double (&wx)[D0 + 1], const double (&wy)[D0 + 1], double wv)
 {
     constexpr int W = Tile<D0>::W;
-    const int rx = rel_cell(cx, bx, m.n[0]), ry = rel_cell(cy, by, m.n[1]);
-    if (__builtin_expect(rx >= -kR2 && rx <= kR2 && ry >= -kR2 && ry <= kR2, 1)) {
-        double *q = tile + (size_t)((ry + kR2) * W + rx + kR2) * 32;
+    double *q = tile + (size_t)(ly * W + lx) * 32;
 #pragma unroll
-        for (int b = 0; b <= D0; ++b) {
-            const double wb = wv * wy[b];
-            double r[D0 + 1];
+    for (int b = 0; b <= D0; ++b) {
+        const double wb = wv * wy[b];
+        double r[D0 + 1];
 #pragma unroll
-            for (int a = 0; a <= D0; ++a) r[a] = q[(b * W + a) * 32];
+        for (int a = 0; a <= D0; ++a) r[a] = q[(b * W + a) * 32];
 #pragma unroll
-            for (int a = 0; a <= D0; ++a) q[(b * W + a) * 32] = fma(wb, wx[a], r[a]);
-        }
-    } else {
-        int ix[D0 + 1], iy[D0 + 1];
-        stencil<D0>(cx, m.n[0], ix);
-        stencil<D0>(cy, m.n[1], iy);
-        for (int b = 0; b <= D0; ++b)
-            for (int a = 0; a <= D0; ++a) atomicAdd(grid + ix[a] + (size_t)iy[b] * m.n[0], (wv * wy[b]) * wx[a]);
+        for (int a = 0; a <= D0; ++a) q[(b * W + a) * 32] = fma(wb, wx[a], r[a]);
     }
+}
+// the same deposit straight to the global grid (particles outside the warp's window)
+template <int D0>
+__device__ __noinline__ void deposit_global(double *__restrict__ grid, int nx, int ny, int cx, int cy, double tx, double ty, double wv)
+{
+    int ix[D0 + 1], iy[D0 + 1];
+    double wx[D0 + 1], wy[D0 + 1];
+    stencil<D0>(cx, nx, ix);
+    stencil<D0>(cy, ny, iy);
+    basis_pp<D0>(tx, wx);
+    basis_pp<D0>(ty, wy);
+    for (int b = 0; b <= D0; ++b)
+        for (int a = 0; a <= D0; ++a) atomicAdd(grid + ix[a] + (size_t)iy[b] * nx, (wv * wy[b]) * wx[a]);
 }
 
 // ---- add_charge!: rho += q w N^p(x1) N^p(x2) ----------------------------------------------------
 template <int D0>
 struct Op2Charge {
     static constexpr bool DEPOSIT = true, WRITE_X = false, WRITE_V = false;
-    static constexpr int D = D0;
+    static constexpr int D = D0, NF = 0;
     struct Params { double wscale; };
-    static __device__ __forceinline__ void apply(Part2 &p, const P2<Op2Charge> &P, double *tile, int bx, int by)
+    static __device__ __forceinline__ void apply(Part2 &p, const P2<Op2Charge> &P, const double *, double *tile, int bx, int by)
     {
         int cx, cy;
-        double tx, ty, bx0[D0 + 1], by0[D0 + 1];
+        double tx, ty;
         locate2<0>(p.x[0], P.m, cx, tx);
         locate2<1>(p.x[1], P.m, cy, ty);
-        basis_pp<D0>(tx, bx0);
-        basis_pp<D0>(ty, by0);
-        deposit_pp<D0>(tile, P.grid, P.m, cx, cy, bx, by, bx0, by0, p.w * P.op.wscale);
+        const int rx = rel_cell(cx, bx, P.m.n[0]), ry = rel_cell(cy, by, P.m.n[1]);
+        const double wv = p.w * P.op.wscale;
+        if (__builtin_expect(rx >= -kR2 && rx <= kR2 && ry >= -kR2 && ry <= kR2, 1)) {
+            double bx0[D0 + 1], by0[D0 + 1];
+            basis_pp<D0>(tx, bx0);
+            basis_pp<D0>(ty, by0);
+            deposit_tile<D0>(tile, rx + kR2, ry + kR2, bx0, by0, wv);
+        } else {
+            deposit_global<D0>(P.grid, P.m.n[0], P.m.n[1], cx, cy, tx, ty, wv);
+        }
     }
 };
 
-// ---- operatorHp3: v1 -= dt q/m v3 B2, v2 += dt q/m v3 B1, j3 += q w v3 dt N N ------------------
+// ---- operatorHp3: v1 -= dt q/m v3 B2, v2 += dt q/m v3 B1, j3 += q w v3 dt N N.  fields: B1 (D0,D1), B2 (D1,D0)
 template <int D0>
 struct Op2Hp3 {
     static constexpr bool DEPOSIT = true, WRITE_X = false, WRITE_V = true;
-    static constexpr int D = D0;
-    struct Params { double dtqm, wscale_dt; };   // fields: f[0] = B1, f[1] = B2
-    static __device__ __forceinline__ void apply(Part2 &p, const P2<Op2Hp3> &P, double *tile, int bx, int by)
+    static constexpr int D = D0, NF = 2;
+    struct Params { double dtqm, wscale_dt; };
+    using PP = P2<Op2Hp3>;
+
+    static __device__ __noinline__ V3 slow(double x, double y, const PP &P)
     {
         constexpr int D1 = D0 - 1;
         int cx, cy, ix[D0 + 1], iy[D0 + 1];
         double tx, ty, bx0[D0 + 1], bx1[D1 + 1], by0[D0 + 1], by1[D1 + 1];
-        locate2<0>(p.x[0], P.m, cx, tx);
-        locate2<1>(p.x[1], P.m, cy, ty);
+        locate2<0>(x, P.m, cx, tx);
+        locate2<1>(y, P.m, cy, ty);
         stencil<D0>(cx, P.m.n[0], ix);
         stencil<D0>(cy, P.m.n[1], iy);
         basis_pp<D0>(tx, bx0); basis_pp<D1>(tx, bx1);
         basis_pp<D0>(ty, by0); basis_pp<D1>(ty, by1);
         const int nx = P.m.n[0];
-        const double B1 = eval2<D0, D1, 0, 1, D0>(P.f[0], nx, ix, iy, bx0, by1);
-        const double B2 = eval2<D1, D0, 1, 0, D0>(P.f[1], nx, ix, iy, bx1, by0);
+        return V3{eval2<D0, D1, 0, 1, D0>(P.f[0], nx, ix, iy, bx0, by1), eval2<D1, D0, 1, 0, D0>(P.f[1], nx, ix, iy, bx1, by0), 0.0};
+    }
+
+    static __device__ __forceinline__ void apply(Part2 &p, const PP &P, const double *ft, double *tile, int bx, int by)
+    {
+        constexpr int D1 = D0 - 1, W = Tile<D0>::W, WW = W * W;
+        int cx, cy;
+        double tx, ty;
+        locate2<0>(p.x[0], P.m, cx, tx);
+        locate2<1>(p.x[1], P.m, cy, ty);
+        const int rx = rel_cell(cx, bx, P.m.n[0]), ry = rel_cell(cy, by, P.m.n[1]);
         const double v3 = p.v[2];
+        const double wv = (p.w * P.op.wscale_dt) * v3;
+        double B1, B2;
+        if (__builtin_expect(rx >= -kR2 && rx <= kR2 && ry >= -kR2 && ry <= kR2, 1)) {
+            double bx0[D0 + 1], bx1[D1 + 1], by0[D0 + 1], by1[D1 + 1];
+            basis_pp<D0>(tx, bx0); basis_pp<D1>(tx, bx1);
+            basis_pp<D0>(ty, by0); basis_pp<D1>(ty, by1);
+            const int lx = rx + kR2, ly = ry + kR2;
+            const double *q = ft + ly * W + lx;
+            B1 = eval_tile<D0, D1, W>(q + W, bx0, by1);
+            B2 = eval_tile<D1, D0, W>(q + WW + 1, bx1, by0);
+            deposit_tile<D0>(tile, lx, ly, bx0, by0, wv);
+        } else {
+            const V3 bb = slow(p.x[0], p.x[1], P);
+            B1 = bb.v0;
+            B2 = bb.v1;
+            deposit_global<D0>(P.grid, P.m.n[0], P.m.n[1], cx, cy, tx, ty, wv);
+        }
         p.v[0] = fma(-(P.op.dtqm * v3), B2, p.v[0]);
         p.v[1] = fma(P.op.dtqm * v3, B1, p.v[1]);
-        deposit_pp<D0>(tile, P.grid, P.m, cx, cy, bx, by, bx0, by0, (p.w * P.op.wscale_dt) * v3);
     }
 };
 
@@ -232,22 +315,24 @@ struct Op2Hp3 {
 template <int D0, int DIR>
 struct Op2Hp12 {
     static constexpr bool DEPOSIT = true, WRITE_X = true, WRITE_V = true;
-    static constexpr int D = D0;
+    static constexpr int D = D0, NF = 2;
     struct Params { double dt, qm_h, wscale_h; };   // h = d[DIR]
     using PP = P2<Op2Hp12>;
 
-    // general path: any displacement, global REDs (rare: more than one cell per step or outside the window)
+    // general path: any displacement, global loads and REDs (rare: more than one cell per step or outside the window)
     struct Sums { double z, o; };
-    static __device__ __noinline__ Sums general(double x_old, double x_new, int ct, const double *bt0, const double *bt1,
-                                               const PP &P, double wq)
+    static __device__ __noinline__ Sums general(double x_old, double x_new, double x_t, const PP &P, double wq)
     {
-        double sum_z = 0.0, sum_o = 0.0;
         constexpr int D1 = D0 - 1, O = 1 - DIR;
         const Mesh2 &m = P.m;
-        int co, cn;
-        double to, tn;
+        double sum_z = 0.0, sum_o = 0.0;
+        int co, cn, ct;
+        double to, tn, tt, bt0[D0 + 1], bt1[D1 + 1];
         locate2<DIR>(x_old, m, co, to);
         locate2<DIR>(x_new, m, cn, tn);
+        locate2<O>(x_t, m, ct, tt);
+        basis_pp<D0>(tt, bt0);
+        basis_pp<D1>(tt, bt1);
         const int step = cn >= co ? 1 : -1;
         for (int c = co;; c += step) {
             double lower, upper, sgn;
@@ -277,9 +362,9 @@ struct Op2Hp12 {
         return Sums{sum_z, sum_o};
     }
 
-    static __device__ __forceinline__ void apply(Part2 &p, const PP &P, double *tile, int bx, int by)
+    static __device__ __forceinline__ void apply(Part2 &p, const PP &P, const double *ft, double *tile, int bx, int by)
     {
-        constexpr int D1 = D0 - 1, O = 1 - DIR, W = Tile<D0>::W;
+        constexpr int D1 = D0 - 1, O = 1 - DIR, W = Tile<D0>::W, WW = W * W;
         const Mesh2 &m = P.m;
         const double x_old = p.x[DIR], x_new = fma(P.op.dt, p.v[DIR], x_old);
         int co, cn, ct;
@@ -287,23 +372,22 @@ struct Op2Hp12 {
         locate2<DIR>(x_old, m, co, to);
         locate2<DIR>(x_new, m, cn, tn);
         locate2<O>(p.x[O], m, ct, tt);
-        double bt0[D0 + 1], bt1[D1 + 1];
-        basis_pp<D0>(tt, bt0);
-        basis_pp<D1>(tt, bt1);
         const double wq = p.w * P.op.wscale_h;
-        double sum_z = 0.0, sum_o = 0.0;
+        double sum_z, sum_o;
         const int base_d = DIR == 0 ? bx : by, base_t = DIR == 0 ? by : bx;
         const int ro = rel_cell(co, base_d, m.n[DIR]), rn = rel_cell(cn, base_d, m.n[DIR]), rt = rel_cell(ct, base_t, m.n[O]);
         const int dc = cn - co;
-        // the window of D1+2 dofs starts at local index rmin + kR2 + 1: cells up to kR2 - 1 keep it inside the tile
-        const bool fast = dc >= -1 && dc <= 1 && ro >= -kR2 && ro < kR2 && rn >= -kR2 && rn < kR2 && rt >= -kR2 && rt <= kR2;
+        // the window of D1+2 dofs starts at local index rmin + kR2 + 1 and must end inside the tile: rmin <= kR2 - 1
+        const int rmin = min(ro, rn);
+        const bool fast = dc >= -1 && dc <= 1 && rmin >= -kR2 && rmin < kR2 && rt >= -kR2 && rt <= kR2;
         if (__builtin_expect(fast, 1)) {
             // window of D1+2 dofs from cmin (see OpStrangFused::work): weight_m = Phi_m(new) - Phi_m(old)
-            double A[D1 + 1], B[D1 + 1], win[D1 + 2];
+            double A[D1 + 1], B[D1 + 1], win[D1 + 2], bt0[D0 + 1], bt1[D1 + 1];
             prim_pp<D1>(to, A);
             prim_pp<D1>(tn, B);
-            const int cmin = min(co, cn);
-            const bool o1 = co != cmin, n1 = cn != cmin;
+            basis_pp<D0>(tt, bt0);
+            basis_pp<D1>(tt, bt1);
+            const bool o1 = co > cn, n1 = cn > co;   // which endpoint sits in the window's second cell
 #pragma unroll
             for (int k = 0; k <= D1 + 1; ++k) {
                 const double F = k <= D1 ? prim_full<D1>(k <= D1 ? k : 0) : 0.0;
@@ -312,46 +396,35 @@ struct Op2Hp12 {
                 const double oo = k == 0 ? F : (k <= D1 ? F + A[k >= 1 ? k - 1 : 0] : A[D1]);
                 win[k] = (n1 ? nn : n0) - (o1 ? oo : o0);
             }
-            // periodic indices: along DIR the window, across DIR the degree-D0 stencil
-            int iw[D1 + 2], it[D0 + 1];
-            {
-                int g = wrapi(cmin - D1, m.n[DIR]);
-#pragma unroll
-                for (int k = 0; k <= D1 + 1; ++k) {
-                    iw[k] = g;
-                    g = g + 1 == m.n[DIR] ? 0 : g + 1;
-                }
-            }
-            stencil<D0>(ct, m.n[O], it);
-            const int nx = m.n[0];
-            const int sd = DIR == 0 ? 1 : nx, st = DIR == 0 ? nx : 1;   // strides along / across DIR
-            // gathers: B3 (transverse D1: it[1..D0]) and the other component (transverse D0)
+            const int lw = rmin + kR2 + (D0 - D1), lt = rt + kR2;
+            // strides of the tile along / across DIR
+            constexpr int sd = DIR == 0 ? 1 : W, st = DIR == 0 ? W : 1;
+            const double *q3 = ft + lw * sd + (lt + 1) * st;        // B3: transverse degree D1
+            const double *qo = ft + WW + lw * sd + lt * st;          // B2 / B1: transverse degree D0
+            sum_z = 0.0;
+            sum_o = 0.0;
 #pragma unroll
             for (int k = 0; k <= D1 + 1; ++k) {
-                double sz = 0.0, so = 0.0;
+                double sz = q3[k * sd] * bt1[0], so = qo[k * sd] * bt0[0];
 #pragma unroll
-                for (int b = 0; b <= D1; ++b) sz = fma(__ldg(P.f[0] + (size_t)iw[k] * sd + (size_t)it[b + 1] * st), bt1[b], sz);
+                for (int b = 1; b <= D1; ++b) sz = fma(q3[k * sd + b * st], bt1[b], sz);
 #pragma unroll
-                for (int b = 0; b <= D0; ++b) so = fma(__ldg(P.f[1] + (size_t)iw[k] * sd + (size_t)it[b] * st), bt0[b], so);
+                for (int b = 1; b <= D0; ++b) so = fma(qo[k * sd + b * st], bt0[b], so);
                 sum_z = fma(sz, win[k], sum_z);
                 sum_o = fma(so, win[k], sum_o);
             }
-            // deposit j[window x stencil]: local window start = rmin + kR2 + 1 (degree D1 = D0-1), stencil rt + kR2
-            const int rmin = min(ro, rn);
-            const int lw = rmin + kR2 + (D0 - D1), lt = rt + kR2;
-            double *q = tile + (size_t)(DIR == 0 ? lt * W + lw : lw * W + lt) * 32;
-            constexpr int qd = (DIR == 0 ? 1 : W) * 32, qt = (DIR == 0 ? W : 1) * 32;
+            double *q = tile + (size_t)(lw * sd + lt * st) * 32;
 #pragma unroll
             for (int b = 0; b <= D0; ++b) {
                 const double wb = wq * bt0[b];
                 double r[D1 + 2];
 #pragma unroll
-                for (int k = 0; k <= D1 + 1; ++k) r[k] = q[b * qt + k * qd];
+                for (int k = 0; k <= D1 + 1; ++k) r[k] = q[(b * st + k * sd) * 32];
 #pragma unroll
-                for (int k = 0; k <= D1 + 1; ++k) q[b * qt + k * qd] = fma(wb, win[k], r[k]);
+                for (int k = 0; k <= D1 + 1; ++k) q[(b * st + k * sd) * 32] = fma(wb, win[k], r[k]);
             }
         } else {
-            const Sums g = general(x_old, x_new, ct, bt0, bt1, P, wq);
+            const Sums g = general(x_old, x_new, p.x[O], P, wq);
             sum_z = g.z;
             sum_o = g.o;
         }
@@ -393,26 +466,57 @@ __device__ __forceinline__ void store2(const Rows2 &r, int64_t i, const Part2 &p
     }
 }
 
+// shared memory of one warp: Op::NF field tiles (W*W doubles each, shared by the lanes) followed by the
+// lane-private deposit tile (W*W*32 doubles)
+template <class Op>
+constexpr size_t warp_smem_doubles()
+{
+    return (size_t)Op::NF * Tile<Op::D>::SLOTS + (Op::DEPOSIT ? (size_t)Tile<Op::D>::SLOTS * 32 : 0);
+}
+
 template <class Op>
 __global__ void __launch_bounds__(kThreads2) k2_pass(const __grid_constant__ P2<Op> P)
 {
     extern __shared__ double smem[];
     constexpr int SLOTS = Tile<Op::D>::SLOTS, W = Tile<Op::D>::W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *wtile = smem + (size_t)warp * SLOTS * 32;
+    double *ftile = smem + (size_t)warp * warp_smem_doubles<Op>();
+    double *wtile = ftile + (size_t)Op::NF * SLOTS;
     double *tile = wtile + lane;
+    const int nx = P.m.n[0], ny = P.m.n[1];
     const int64_t n_chunks = (P.n + P.chunk - 1) / P.chunk;
     for (int64_t ch = (int64_t)blockIdx.x * kWarps2 + warp; ch < n_chunks; ch += (int64_t)gridDim.x * kWarps2) {
         const int64_t lo = ch * P.chunk, hi = min(P.n, lo + P.chunk);
-        int bx = 0, by = 0;
-        if (Op::DEPOSIT) {
+        // window base = mean cell of 32 particles spread evenly over the chunk (a sorted chunk spans one or two
+        // cells plus the drift since the sort, so the mean centres the window); then stage the field tiles
+        int bx, by;
+        {
+            const int64_t is = lo + (int64_t)lane * ((hi - lo + 31) / 32);
+            const int64_t ic = is < hi ? is : lo;
             double t;
-            locate2<0>(P.r.x[0][lo], P.m, bx, t);
-            locate2<1>(P.r.x[1][lo], P.m, by, t);
-            bx = wrapi(bx, P.m.n[0]);
-            by = wrapi(by, P.m.n[1]);
-            for (int s = 0; s < SLOTS; ++s) tile[s * 32] = 0.0;
+            int cx, cy;
+            locate2<0>(P.r.x[0][ic], P.m, cx, t);
+            locate2<1>(P.r.x[1][ic], P.m, cy, t);
+            const int cx0 = wrapi(__shfl_sync(0xffffffffu, cx, 0), nx), cy0 = wrapi(__shfl_sync(0xffffffffu, cy, 0), ny);
+            int sx = rel_cell(wrapi(cx, nx), cx0, nx), sy = rel_cell(wrapi(cy, ny), cy0, ny);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                sx += __shfl_xor_sync(0xffffffffu, sx, off);
+                sy += __shfl_xor_sync(0xffffffffu, sy, off);
+            }
+            bx = wrapi(cx0 + __float2int_rn((float)sx * (1.0f / 32.0f)), nx);
+            by = wrapi(cy0 + __float2int_rn((float)sy * (1.0f / 32.0f)), ny);
         }
+        const int ox = bx - kR2 - Op::D, oy = by - kR2 - Op::D;
+        for (int s = lane; s < SLOTS; s += 32) {
+            const int ly = s / W, lx = s - ly * W;
+            const size_t g = (size_t)wrapi(ox + lx, nx) + (size_t)wrapi(oy + ly, ny) * nx;
+#pragma unroll
+            for (int f = 0; f < Op::NF; ++f) ftile[f * SLOTS + s] = P.f[f][g];
+        }
+        if (Op::DEPOSIT)
+            for (int s = 0; s < SLOTS; ++s) tile[s * 32] = 0.0;
+        __syncwarp();
         int64_t i = lo + lane;
         Part2 a, b;
         bool ha = i < hi, hb = i + 32 < hi;
@@ -424,27 +528,26 @@ __global__ void __launch_bounds__(kThreads2) k2_pass(const __grid_constant__ P2<
             Part2 c, d;
             if (hc) load2<Op>(P.r, ni, c);
             if (hd) load2<Op>(P.r, ni + 32, d);
-            Op::apply(a, P, tile, bx, by);
+            Op::apply(a, P, ftile, tile, bx, by);
             store2<Op>(P.r, i, a);
             if (hb) {
-                Op::apply(b, P, tile, bx, by);
+                Op::apply(b, P, ftile, tile, bx, by);
                 store2<Op>(P.r, i + 32, b);
             }
             a = c; b = d;
             ha = hc; hb = hd;
             i = ni;
         }
+        __syncwarp();
         if (Op::DEPOSIT) {
-            __syncwarp();
             // sum the 32 lane copies of every slot (rotated: conflict free) and add to the global grid
-            const int ox = bx - kR2 - Op::D, oy = by - kR2 - Op::D;
             for (int s = lane; s < SLOTS; s += 32) {
                 double sum = 0.0;
 #pragma unroll 8
                 for (int l = 0; l < 32; ++l) sum += wtile[(size_t)s * 32 + ((l + lane) & 31)];
                 if (sum != 0.0) {
                     const int ly = s / W, lx = s - ly * W;
-                    atomicAdd(P.grid + wrapi(ox + lx, P.m.n[0]) + (size_t)wrapi(oy + ly, P.m.n[1]) * P.m.n[0], sum);
+                    atomicAdd(P.grid + wrapi(ox + lx, nx) + (size_t)wrapi(oy + ly, ny) * nx, sum);
                 }
             }
             __syncwarp();
@@ -504,7 +607,7 @@ static void launch2(Splitting2D &h, P2<Op> P, const char *tag)
     P.n = h.pg->n;
     P.m = mesh2(*h.maxwell);
     if (P.n <= 0) return;
-    const size_t smem = Op::DEPOSIT ? (size_t)kWarps2 * Tile<Op::D>::SLOTS * 32 * sizeof(double) : 0;
+    const size_t smem = (size_t)kWarps2 * warp_smem_doubles<Op>() * sizeof(double);
     static bool configured = false;
     if (!configured && smem > 48 * 1024) {
         GP_CUDA(cudaFuncSetAttribute(k2_pass<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -223,37 +223,60 @@ __device__ __forceinline__ int sort_cell2(double x, double y, const SortMesh2 &m
     cy = min(max(cy, 0), m.n[1] - 1);
     return cx + cy * m.n[0];
 }
-__global__ void k_sort2_hist(const double *__restrict__ x, const double *__restrict__ y, int64_t n, SortMesh2 m,
-                             int *__restrict__ hist)
+// per-block histogram of a contiguous chunk: shared counters (warp-aggregated), one row of `blockhist` per block,
+// non-zero entries added to the global histogram
+__global__ void __launch_bounds__(256) k_sort2_hist(const double *__restrict__ x, const double *__restrict__ y, int64_t n,
+                                                    int64_t per_block, SortMesh2 m, int ncell, int *__restrict__ hist,
+                                                    int *__restrict__ blockhist)
 {
+    extern __shared__ int sh[];
+    for (int i = threadIdx.x; i < ncell; i += 256) sh[i] = 0;
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int64_t T = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += T) {
+    const int64_t lo = (int64_t)blockIdx.x * per_block, hi = min(n, lo + per_block);
+    for (int64_t base = lo + (threadIdx.x & ~31); base < hi; base += 256) {
         const int64_t i = base + lane;
-        const bool active = i < n;
+        const bool active = i < hi;
         const unsigned amask = __ballot_sync(0xffffffffu, active);
         if (active) {
             const int cell = sort_cell2(x[i], y[i], m);
             const unsigned peers = __match_any_sync(amask, cell);
-            if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&hist[cell], __popc(peers));
+            if ((peers & ((1u << lane) - 1u)) == 0) atomicAdd(&sh[cell], __popc(peers));
         }
     }
+    __syncthreads();
+    int *row = blockhist + (size_t)blockIdx.x * ncell;
+    for (int i = threadIdx.x; i < ncell; i += 256) {
+        const int c = sh[i];
+        row[i] = c;
+        if (c) atomicAdd(&hist[i], c);
+    }
 }
-__global__ void k_sort2_scatter(const double *__restrict__ src, double *__restrict__ dst, size_t stride, int rows, int64_t n,
-                                SortMesh2 m, int *__restrict__ cursor)
+
+// scatter of the same chunk: reserve [cursor, cursor + count) per cell for this block, then place the particles
+__global__ void __launch_bounds__(256) k_sort2_scatter(const double *__restrict__ src, double *__restrict__ dst, size_t stride,
+                                                       int rows, int64_t n, int64_t per_block, SortMesh2 m, int ncell,
+                                                       int *__restrict__ cursor, const int *__restrict__ blockhist)
 {
+    extern __shared__ int sh[];   // next free slot of every cell for this block
+    const int *row = blockhist + (size_t)blockIdx.x * ncell;
+    for (int i = threadIdx.x; i < ncell; i += 256) {
+        const int c = row[i];
+        sh[i] = c ? atomicAdd(&cursor[i], c) : 0;
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int64_t T = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += T) {
+    const int64_t lo = (int64_t)blockIdx.x * per_block, hi = min(n, lo + per_block);
+    for (int64_t base = lo + (threadIdx.x & ~31); base < hi; base += 256) {
         const int64_t i = base + lane;
-        const bool active = i < n;
+        const bool active = i < hi;
         const unsigned amask = __ballot_sync(0xffffffffu, active);
         if (active) {
             const int cell = sort_cell2(src[i], src[stride + i], m);
             const unsigned peers = __match_any_sync(amask, cell);
             const int leader = __ffs(peers) - 1;
             int start = 0;
-            if (lane == leader) start = atomicAdd(&cursor[cell], __popc(peers));
+            if (lane == leader) start = atomicAdd(&sh[cell], __popc(peers));
             start = __shfl_sync(peers, start, leader);
             const int64_t d = (int64_t)start + __popc(peers & ((1u << lane) - 1u));
             for (int r = 0; r < rows; ++r) dst[(size_t)r * stride + d] = src[(size_t)r * stride + i];
@@ -272,16 +295,31 @@ void pg_sort_2d(ParticleGroup &pg, const Maxwell2D &mx)
     m.inv_d[0] = 1.0 / mx.dx; m.inv_d[1] = 1.0 / mx.dy;
     m.n[0] = mx.nx; m.n[1] = mx.ny;
     const int64_t cells = (int64_t)mx.nx * mx.ny;
-    if (pg.sort_keys.n < (size_t)cells) pg.sort_keys.alloc((size_t)cells);
+    const size_t smem = (size_t)cells * sizeof(int);
+    GP_REQUIRE(smem <= 200 * 1024, GEMPIC_EINVAL, "2D cell sort supports up to 51200 cells (%lld requested)", (long long)cells);
+    const int grid = (int)std::min<int64_t>((int64_t)c.sm_count * 8, (pg.n + 255) / 256);
+    int64_t per_block = (pg.n + grid - 1) / grid;
+    per_block = (per_block + 255) / 256 * 256;
+    const size_t need = (size_t)cells * ((size_t)grid + 1);
+    if (pg.sort_keys.n < need) pg.sort_keys.alloc(need);
     if (pg.sort_tmp.n < pg.data.n) pg.sort_tmp.alloc(pg.data.n);
-    GP_CUDA(cudaMemsetAsync(pg.sort_keys.p, 0, sizeof(int) * cells, c.stream));
-    const int grid = c.sm_count * 8;
-    k_sort2_hist<<<grid, 256, 0, c.stream>>>(pg.row(0), pg.row(1), pg.n, m, pg.sort_keys.p);
+    int *hist = pg.sort_keys.p, *blockhist = pg.sort_keys.p + cells;
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        GP_CUDA(cudaFuncSetAttribute(k_sort2_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        GP_CUDA(cudaFuncSetAttribute(k_sort2_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    GP_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * cells, c.stream));
+    profile_begin("cell sort 2d");
+    k_sort2_hist<<<grid, 256, smem, c.stream>>>(pg.row(0), pg.row(1), pg.n, per_block, m, (int)cells, hist, blockhist);
     GP_CUDA(cudaGetLastError());
-    k_sort_scan<<<1, 1024, 0, c.stream>>>(pg.sort_keys.p, cells);
+    k_sort_scan<<<1, 1024, 0, c.stream>>>(hist, cells);
     GP_CUDA(cudaGetLastError());
-    k_sort2_scatter<<<grid, 256, 0, c.stream>>>(pg.data.p, pg.sort_tmp.p, pg.stride, pg.rows(), pg.n, m, pg.sort_keys.p);
+    k_sort2_scatter<<<grid, 256, smem, c.stream>>>(pg.data.p, pg.sort_tmp.p, pg.stride, pg.rows(), pg.n, per_block, m,
+                                                   (int)cells, hist, blockhist);
     GP_CUDA(cudaGetLastError());
+    profile_end("cell sort 2d");
     count_launch(3);
     GP_CUDA(cudaStreamSynchronize(c.stream));
     std::swap(pg.data.p, pg.sort_tmp.p);
