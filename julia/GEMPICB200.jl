@@ -10,7 +10,8 @@
 #   using GEMPICB200   # instead of `using GEMPIC` for the types below
 module GEMPICB200
 
-export OneDGrid, ParticleGroup, ParticleMeshCoupling1D, Maxwell1DFEM,
+export OneDGrid, TwoDGrid, ParticleGroup, ParticleMeshCoupling1D, Maxwell1DFEM, TwoDMaxwell, HamiltonianSplitting2D3V,
+       operatorHp3, compute_rho_from_e!, compute_rhs_from_function, l2projection, charge_density,
        HamiltonianSplitting, HamiltonianSplittingBoris, strang_splitting!, staggering!,
        operatorHp1, operatorHp2, operatorHE, operatorHB, solve_poisson!,
        add_charge!, evaluate, add_current_update_v!, compute_e_from_rho!, compute_e_from_j!,
@@ -248,6 +249,100 @@ staggering!(h::HamiltonianSplittingBoris, dt::Float64) =                     # :
 strang_splitting!(h::HamiltonianSplittingBoris, dt::Float64, number_steps::Int) =   # :132-177
     check(ccall((:gempic_boris_strang_splitting_host, LIB), Cint, (Handle, Cdouble, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
                 h.handle, dt, number_steps, h.e_dofs[1], h.e_dofs[2], h.b_dofs))
+
+# ---- TwoDGrid / TwoDMaxwell (src/mesh.jl:17-45, src/maxwell_2d_fem.jl:11-87) --------------------
+struct TwoDGrid
+    nx::Int
+    ny::Int
+    xmin::Float64
+    xmax::Float64
+    ymin::Float64
+    ymax::Float64
+    TwoDGrid(xmin, xmax, nx::Int, ymin, ymax, ny::Int) = new(nx, ny, xmin, xmax, ymin, ymax)
+end
+mutable struct TwoDMaxwell
+    s_deg_0::Int
+    s_deg_1::Int
+    mesh::TwoDGrid
+    handle::Handle
+    function TwoDMaxwell(mesh::TwoDGrid, degree::Int)
+        init()
+        h = Ref{Handle}(0)
+        check(ccall((:gempic_maxwell2d_create, LIB), Cint, (Cdouble, Cdouble, Cint, Cdouble, Cdouble, Cint, Cint, Ref{Handle}),
+                    mesh.xmin, mesh.xmax, mesh.nx, mesh.ymin, mesh.ymax, mesh.ny, degree, h))
+        m = new(degree, degree - 1, mesh, h[])
+        finalizer(q -> ccall((:gempic_maxwell2d_destroy, LIB), Cint, (Handle,), q.handle), m)
+        return m
+    end
+end
+const Dofs3 = Vector{Vector{Float64}}
+compute_e_from_rho!(e::Dofs3, m::TwoDMaxwell, rho::Vector{Float64}) =                      # :199-201
+    check(ccall((:gempic_maxwell2d_compute_e_from_rho, LIB), Cint, (Handle, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), m.handle, e[1], e[2], rho))
+compute_e_from_b!(e::Dofs3, m::TwoDMaxwell, dt::Float64, b::Dofs3) =                       # :370-412
+    check(ccall((:gempic_maxwell2d_compute_e_from_b, LIB), Cint, (Handle, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                m.handle, e[1], e[2], e[3], dt, b[1], b[2], b[3]))
+compute_b_from_e!(b::Dofs3, m::TwoDMaxwell, dt::Float64, e::Dofs3) =                       # :423-444
+    check(ccall((:gempic_maxwell2d_compute_b_from_e, LIB), Cint, (Handle, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                m.handle, b[1], b[2], b[3], dt, e[1], e[2], e[3]))
+compute_e_from_j!(e::Vector{Float64}, m::TwoDMaxwell, current::Vector{Float64}, component::Int) =   # :455-459
+    check(ccall((:gempic_maxwell2d_compute_e_from_j, LIB), Cint, (Handle, Ptr{Cdouble}, Ptr{Cdouble}, Cint), m.handle, e, current, component))
+compute_rho_from_e!(rho::Vector{Float64}, m::TwoDMaxwell, e::Dofs3) =                       # :468-500
+    check(ccall((:gempic_maxwell2d_compute_rho_from_e, LIB), Cint, (Handle, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), m.handle, rho, e[1], e[2], e[3]))
+function inner_product(m::TwoDMaxwell, c1::Vector{Float64}, c2::Vector{Float64}, component, form)   # :512-575
+    out = Ref{Cdouble}(0)
+    check(ccall((:gempic_maxwell2d_inner_product, LIB), Cint, (Handle, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Cint, Ref{Cdouble}),
+                m.handle, c1, c2, component, form, out))
+    return out[]
+end
+_tramp2(x::Cdouble, y::Cdouble, ctx::Ptr{Cvoid})::Cdouble = unsafe_pointer_to_objref(ctx)[](x, y)
+function compute_rhs_from_function(m::TwoDMaxwell, f::Function, component::Int, form::Int)   # :124-196
+    coefs = zeros(m.mesh.nx * m.mesh.ny)
+    r = Ref{Function}(f)
+    GC.@preserve r check(ccall((:gempic_maxwell2d_compute_rhs_from_function, LIB), Cint, (Handle, Ptr{Cdouble}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint),
+                               m.handle, coefs, @cfunction(_tramp2, Cdouble, (Cdouble, Cdouble, Ptr{Cvoid})), pointer_from_objref(r), component, form))
+    return coefs
+end
+function l2projection(m::TwoDMaxwell, f::Function, component::Int, form::Int)                # :283-293
+    coefs = zeros(m.mesh.nx * m.mesh.ny)
+    r = Ref{Function}(f)
+    GC.@preserve r check(ccall((:gempic_maxwell2d_l2projection, LIB), Cint, (Handle, Ptr{Cdouble}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint),
+                               m.handle, coefs, @cfunction(_tramp2, Cdouble, (Cdouble, Cdouble, Ptr{Cvoid})), pointer_from_objref(r), component, form))
+    return coefs
+end
+
+# ---- HamiltonianSplitting{2,3}: the content of the reference's empty src/hamiltonian_splitting_2d3v.jl ----
+# Same field names and operator methods as HamiltonianSplitting{1,2}; e_dofs / b_dofs are three aliased
+# nx*ny vectors each.  strang_splitting! = HB HE Hp3 Hp2 Hp1 Hp2 Hp3 HE HB.
+struct HamiltonianSplitting2D3V
+    dims::Tuple{Int64,Int64}
+    maxwell_solver::TwoDMaxwell
+    particle_group::ParticleGroup
+    e_dofs::Dofs3
+    b_dofs::Dofs3
+    handle::Handle
+    function HamiltonianSplitting2D3V(maxwell_solver::TwoDMaxwell, particle_group::ParticleGroup{2,3}, e_dofs::Dofs3, b_dofs::Dofs3)
+        h = Ref{Handle}(0)
+        check(ccall((:gempic_hs2d_create, LIB), Cint, (Handle, Handle, Ref{Handle}), maxwell_solver.handle, particle_group.handle, h))
+        return new((2, 3), maxwell_solver, particle_group, e_dofs, b_dofs, h[])
+    end
+end
+const OP_HP3 = Cint(5)
+_op(h::HamiltonianSplitting2D3V, op::Cint, dt::Float64) =
+    check(ccall((:gempic_hs2d_operator_host, LIB), Cint, (Handle, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                h.handle, op, dt, h.e_dofs[1], h.e_dofs[2], h.e_dofs[3], h.b_dofs[1], h.b_dofs[2], h.b_dofs[3]))
+operatorHp1(h::HamiltonianSplitting2D3V, dt::Float64) = _op(h, OP_HP1, dt)
+operatorHp2(h::HamiltonianSplitting2D3V, dt::Float64) = _op(h, OP_HP2, dt)
+operatorHp3(h::HamiltonianSplitting2D3V, dt::Float64) = _op(h, OP_HP3, dt)
+operatorHE(h::HamiltonianSplitting2D3V, dt::Float64) = _op(h, OP_HE, dt)
+operatorHB(h::HamiltonianSplitting2D3V, dt::Float64) = _op(h, OP_HB, dt)
+strang_splitting!(h::HamiltonianSplitting2D3V, dt::Float64, number_steps::Int) =
+    check(ccall((:gempic_hs2d_strang_splitting_host, LIB), Cint, (Handle, Cdouble, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                h.handle, dt, number_steps, h.e_dofs[1], h.e_dofs[2], h.e_dofs[3], h.b_dofs[1], h.b_dofs[2], h.b_dofs[3]))
+function charge_density(h::HamiltonianSplitting2D3V)
+    rho = zeros(h.maxwell_solver.mesh.nx * h.maxwell_solver.mesh.ny)
+    check(ccall((:gempic_hs2d_charge_density, LIB), Cint, (Handle, Ptr{Cdouble}), h.handle, rho))
+    return rho
+end
 
 # ---- diagnostics (src/diagnostics.jl) --------------------------------------------------------------
 function solve_poisson!(efield::Vector{Float64}, particle_group::ParticleGroup, kernel_smoother_0::ParticleMeshCoupling1D,
