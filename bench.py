@@ -61,7 +61,7 @@ WORKLOADS["2d3v"] = dict(name="2d3v HamiltonianSplitting with TwoDMaxwell, 64x64
                          L=4 * math.pi, sigma=(1.0, 1.0, 1.0), kind="landau", alpha=0.5, k=0.5, integrator="hs2d")
 NX2 = 64
 # 2d3v rows x1,x2,v1,v2,v3,w: HE 40 R + 24 W, Hp3 48 R + 16 W, Hp1/Hp2 48 R + 24 W; sort 2 x 48 + keys
-BYTES2 = {"operatorHE{2,3}": 64, "operatorHp3{2,3}": 64, "operatorHp1{2,3}": 72, "operatorHp2{2,3}": 72, "cell sort 2d": 112,
+BYTES2 = {"fused[HE,Hp3]{2,3}": 72, "fused[HE,HE,Hp3]{2,3}": 72, "operatorHE{2,3}": 64, "operatorHp3{2,3}": 64, "operatorHp1{2,3}": 72, "operatorHp2{2,3}": 72, "cell sort 2d": 112,
           "strang_step": 2 * 64 + 2 * 64 + 3 * 72}
 # algorithmic DRAM bytes per particle of each pass (fp64 SoA rows x, v1, v2, w; SURVEY section 8d / DESIGN.md)
 BYTES = {"operatorHE": 40, "operatorHp2": 40, "operatorHp1": 48, "strang_step": 208,
@@ -256,6 +256,7 @@ def run_ours_2d(args):
     e, b = [np.zeros(nd) for _ in range(3)], [np.zeros(nd) for _ in range(3)]
     h = gp.HamiltonianSplitting2D3V(mx, pg, e, b, resident=True)
     h.set_sort_interval(args.sort_interval)
+    h.set_fusion(bool(args.fuse))
     rho = h.charge_density()
     total_charge = float(rho.sum())
     mx.compute_e_from_rho(e, rho - rho.mean())
@@ -299,6 +300,7 @@ def run_ours_2d(args):
     h.sync_fields()
     h_host = gp.HamiltonianSplitting2D3V(mx, pg, e, b, resident=False)
     h_host.set_sort_interval(args.sort_interval)
+    h_host.set_fusion(bool(args.fuse))
     for _ in range(2):
         h_host.strang_splitting(DT, 1)
     dc.barrier(); gp.synchronize()
@@ -339,7 +341,8 @@ def run_ours_2d(args):
         cfg = {"workload": wl["name"], "particles_per_gpu": int(n_local), "n_cells": [NX2, NX2], "spline_degree": [DEG, DEG - 1],
                "dt": DT, "parallelism": f"particles sharded over {dc.world_size} GPU(s), NCCL allreduce of j1/j2/j3",
                "l2_policy": "inputs (48 B/particle x N >> 126 MB L2) stream from HBM every pass; no flush needed",
-               "kernels": f"one pass per operator (HE, Hp3, Hp2, Hp1, Hp2, Hp3, HE), cell sort every {args.sort_interval} step(s)"}
+               "kernels": ("fused [HE,(HE,)Hp3] + Hp2, Hp1, Hp2, Hp3 passes, one strang_splitting!(h, dt, K) call" if args.fuse else
+                           "one pass per operator (HE, Hp3, Hp2, Hp1, Hp2, Hp3, HE)") + f", cell sort every {args.sort_interval} step(s)"}
         emit({"metric": "particle-steps/s per Strang step", "value": value, "unit": "particle-steps/s", "n_gpus": dc.world_size,
               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,

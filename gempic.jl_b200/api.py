@@ -581,6 +581,9 @@ class HamiltonianSplitting2D3V(_Handle):
     def set_sort_interval(self, interval: int):
         check(_L().gempic_hs2d_set_sort_interval(self._h, C.c_int(interval)))
 
+    def set_fusion(self, fuse: bool):
+        check(_L().gempic_hs2d_set_fusion(self._h, C.c_int(1 if fuse else 0)))
+
     def _op(self, op, dt):
         pg = self.particle_group
         pg._flush()

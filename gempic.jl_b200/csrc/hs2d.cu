@@ -119,7 +119,7 @@ struct P2 {
     int64_t n;
     int64_t chunk;
     Mesh2 m;
-    const double *f[3];
+    const double *f[8];
     double *grid;   // deposit target (nx*ny), zeroed by the launcher
     typename Op::Params op;
 };
@@ -152,6 +152,7 @@ struct V3 { double v0, v1, v2; };
 // ---- operatorHE: v += dt q/m E(x).  fields: E1 (D1,D0), E2 (D0,D1), E3 (D0,D0) ------------------------
 template <int D0>
 struct Op2HE {
+    static __device__ __forceinline__ double stage(const P2<Op2HE> &P, int f, size_t g) { return P.f[f][g]; }
     static constexpr bool DEPOSIT = false, WRITE_X = false, WRITE_V = true;
     static constexpr int D = D0, NF = 3;
     struct Params { double dtqm; };
@@ -232,6 +233,7 @@ __device__ __noinline__ void deposit_global(double *__restrict__ grid, int nx, i
 // ---- add_charge!: rho += q w N^p(x1) N^p(x2) ----------------------------------------------------
 template <int D0>
 struct Op2Charge {
+    static __device__ __forceinline__ double stage(const P2<Op2Charge> &P, int f, size_t g) { return P.f[f][g]; }
     static constexpr bool DEPOSIT = true, WRITE_X = false, WRITE_V = false;
     static constexpr int D = D0, NF = 0;
     struct Params { double wscale; };
@@ -257,6 +259,7 @@ struct Op2Charge {
 // ---- operatorHp3: v1 -= dt q/m v3 B2, v2 += dt q/m v3 B1, j3 += q w v3 dt N N.  fields: B1 (D0,D1), B2 (D1,D0)
 template <int D0>
 struct Op2Hp3 {
+    static __device__ __forceinline__ double stage(const P2<Op2Hp3> &P, int f, size_t g) { return P.f[f][g]; }
     static constexpr bool DEPOSIT = true, WRITE_X = false, WRITE_V = true;
     static constexpr int D = D0, NF = 2;
     struct Params { double dtqm, wscale_dt; };
@@ -308,12 +311,106 @@ struct Op2Hp3 {
     }
 };
 
+// ---- fused [HE x NHE, Hp3]: the leading HE and Hp3 of a Strang step act at the same position, and for NHE = 2 the
+// trailing HE of the previous step is folded in as well (it is separated from the leading HE by field-only updates).
+// The NHE kicks are linear in the dofs, so the staged tiles hold E_c = sum_h dt_h q/m e_c^(h): one gather per component.
+//   source fields: f[0..2] = e (current), f[3..5] = e snapshot before the trailing HE (NHE = 2), f[6] = B1, f[7] = B2
+//   staged tiles : E1 E2 E3 B1 B2
+template <int D0, int NHE>
+struct Op2HEHp3 {
+    static constexpr bool DEPOSIT = true, WRITE_X = false, WRITE_V = true;
+    static constexpr int D = D0, NF = 5;
+    struct Params { double dtqm_e[2], dtqm, wscale_dt; };
+    using PP = P2<Op2HEHp3>;
+    static __device__ __forceinline__ double stage(const PP &P, int f, size_t g)
+    {
+        if (f >= 3) return P.f[3 + f][g];
+        double c = P.op.dtqm_e[0] * P.f[f][g];
+        if (NHE == 2) c = fma(P.op.dtqm_e[1], P.f[3 + f][g], c);
+        return c;
+    }
+
+    struct Out { double e0, e1, e2; };
+    // E kicks from global memory (particle outside the window); B and the deposit follow in slow_b
+    static __device__ __noinline__ Out slow_e(double x, double y, const PP &P)
+    {
+        constexpr int D1 = D0 - 1;
+        int cx, cy, ix[D0 + 1], iy[D0 + 1];
+        double tx, ty, bx0[D0 + 1], bx1[D1 + 1], by0[D0 + 1], by1[D1 + 1];
+        locate2<0>(x, P.m, cx, tx);
+        locate2<1>(y, P.m, cy, ty);
+        stencil<D0>(cx, P.m.n[0], ix);
+        stencil<D0>(cy, P.m.n[1], iy);
+        basis_pp<D0>(tx, bx0); basis_pp<D1>(tx, bx1);
+        basis_pp<D0>(ty, by0); basis_pp<D1>(ty, by1);
+        const int nx = P.m.n[0];
+        Out o{0.0, 0.0, 0.0};
+        for (int h = 0; h < NHE; ++h) {
+            o.e0 = fma(P.op.dtqm_e[h], eval2<D1, D0, 1, 0, D0>(P.f[3 * h + 0], nx, ix, iy, bx1, by0), o.e0);
+            o.e1 = fma(P.op.dtqm_e[h], eval2<D0, D1, 0, 1, D0>(P.f[3 * h + 1], nx, ix, iy, bx0, by1), o.e1);
+            o.e2 = fma(P.op.dtqm_e[h], eval2<D0, D0, 0, 0, D0>(P.f[3 * h + 2], nx, ix, iy, bx0, by0), o.e2);
+        }
+        return o;
+    }
+    static __device__ __noinline__ Out slow_b(double x, double y, const PP &P)
+    {
+        constexpr int D1 = D0 - 1;
+        int cx, cy, ix[D0 + 1], iy[D0 + 1];
+        double tx, ty, bx0[D0 + 1], bx1[D1 + 1], by0[D0 + 1], by1[D1 + 1];
+        locate2<0>(x, P.m, cx, tx);
+        locate2<1>(y, P.m, cy, ty);
+        stencil<D0>(cx, P.m.n[0], ix);
+        stencil<D0>(cy, P.m.n[1], iy);
+        basis_pp<D0>(tx, bx0); basis_pp<D1>(tx, bx1);
+        basis_pp<D0>(ty, by0); basis_pp<D1>(ty, by1);
+        const int nx = P.m.n[0];
+        return Out{eval2<D0, D1, 0, 1, D0>(P.f[6], nx, ix, iy, bx0, by1), eval2<D1, D0, 1, 0, D0>(P.f[7], nx, ix, iy, bx1, by0), 0.0};
+    }
+
+    static __device__ __forceinline__ void apply(Part2 &p, const PP &P, const double *ft, double *tile, int bx, int by)
+    {
+        constexpr int D1 = D0 - 1, W = Tile<D0>::W, WW = W * W;
+        int cx, cy;
+        double tx, ty;
+        locate2<0>(p.x[0], P.m, cx, tx);
+        locate2<1>(p.x[1], P.m, cy, ty);
+        const int rx = rel_cell(cx, bx, P.m.n[0]), ry = rel_cell(cy, by, P.m.n[1]);
+        if (__builtin_expect(rx >= -kR2 && rx <= kR2 && ry >= -kR2 && ry <= kR2, 1)) {
+            double bx0[D0 + 1], bx1[D1 + 1], by0[D0 + 1], by1[D1 + 1];
+            basis_pp<D0>(tx, bx0); basis_pp<D1>(tx, bx1);
+            basis_pp<D0>(ty, by0); basis_pp<D1>(ty, by1);
+            const int lx = rx + kR2, ly = ry + kR2;
+            const double *q = ft + ly * W + lx;
+            p.v[0] += eval_tile<D1, D0, W>(q + 1, bx1, by0);
+            p.v[1] += eval_tile<D0, D1, W>(q + WW + W, bx0, by1);
+            p.v[2] += eval_tile<D0, D0, W>(q + 2 * WW, bx0, by0);
+            const double v3 = p.v[2];
+            const double B1 = eval_tile<D0, D1, W>(q + 3 * WW + W, bx0, by1);
+            const double B2 = eval_tile<D1, D0, W>(q + 4 * WW + 1, bx1, by0);
+            p.v[0] = fma(-(P.op.dtqm * v3), B2, p.v[0]);
+            p.v[1] = fma(P.op.dtqm * v3, B1, p.v[1]);
+            deposit_tile<D0>(tile, lx, ly, bx0, by0, (p.w * P.op.wscale_dt) * v3);
+        } else {
+            const Out e = slow_e(p.x[0], p.x[1], P);
+            p.v[0] += e.e0;
+            p.v[1] += e.e1;
+            p.v[2] += e.e2;
+            const double v3 = p.v[2];
+            const Out bb = slow_b(p.x[0], p.x[1], P);
+            p.v[0] = fma(-(P.op.dtqm * v3), bb.e1, p.v[0]);
+            p.v[1] = fma(P.op.dtqm * v3, bb.e0, p.v[1]);
+            deposit_global<D0>(P.grid, P.m.n[0], P.m.n[1], cx, cy, tx, ty, (p.w * P.op.wscale_dt) * v3);
+        }
+    }
+};
+
 // ---- operatorHp1 (DIR = 0) / operatorHp2 (DIR = 1) ------------------------------------------------
 // f[0] = B3, f[1] = B2 (DIR 0) or B1 (DIR 1).  Along DIR the degree-(p-1) splines are integrated over the
 // straight path x_old -> x_new (primitive form, splines.cuh prim_pp; window of p+1 dofs from the lower cell
 // as in OpStrangFused); across DIR the degree-p (j, B2/B1) and degree-(p-1) (B3) splines are evaluated.
 template <int D0, int DIR>
 struct Op2Hp12 {
+    static __device__ __forceinline__ double stage(const P2<Op2Hp12> &P, int f, size_t g) { return P.f[f][g]; }
     static constexpr bool DEPOSIT = true, WRITE_X = true, WRITE_V = true;
     static constexpr int D = D0, NF = 2;
     struct Params { double dt, qm_h, wscale_h; };   // h = d[DIR]
@@ -475,7 +572,7 @@ constexpr size_t warp_smem_doubles()
 }
 
 template <class Op>
-__global__ void __launch_bounds__(kThreads2) k2_pass(const __grid_constant__ P2<Op> P)
+__global__ void __launch_bounds__(kThreads2, 3) k2_pass(const __grid_constant__ P2<Op> P)
 {
     extern __shared__ double smem[];
     constexpr int SLOTS = Tile<Op::D>::SLOTS, W = Tile<Op::D>::W;
@@ -512,7 +609,7 @@ __global__ void __launch_bounds__(kThreads2) k2_pass(const __grid_constant__ P2<
             const int ly = s / W, lx = s - ly * W;
             const size_t g = (size_t)wrapi(ox + lx, nx) + (size_t)wrapi(oy + ly, ny) * nx;
 #pragma unroll
-            for (int f = 0; f < Op::NF; ++f) ftile[f * SLOTS + s] = P.f[f][g];
+            for (int f = 0; f < Op::NF; ++f) ftile[f * SLOTS + s] = Op::stage(P, f, g);
         }
         if (Op::DEPOSIT)
             for (int s = 0; s < SLOTS; ++s) tile[s * 32] = 0.0;
@@ -720,8 +817,77 @@ void hs2d_operator(Splitting2D &h, int op, double dt)
     }
 }
 
+// [HE x n_he, Hp3](dt/2) in one pass + the e3 solve; n_he = 2 reads the snapshot eT of the trailing HE's field
+static void fused_he_hp3(Splitting2D &h, double dt, int n_he)
+{
+    zero_grid(h.j(2), h.nd);
+    const double qm = h.pg->q_over_m;
+    GP_DISPATCH_D0(h.maxwell->s_deg_0, {
+        if (n_he == 1) {
+            P2<Op2HEHp3<D0, 1>> P{};
+            for (int c = 0; c < 3; ++c) P.f[c] = h.e(c);
+            P.f[6] = h.b(0); P.f[7] = h.b(1);
+            P.grid = h.j(2);
+            P.op.dtqm_e[0] = P.op.dtqm_e[1] = 0.5 * dt * qm;
+            P.op.dtqm = 0.5 * dt * qm;
+            P.op.wscale_dt = h.pg->charge * h.pg->common_weight * 0.5 * dt;
+            launch2(h, P, "fused[HE,Hp3]{2,3}");
+        } else {
+            P2<Op2HEHp3<D0, 2>> P{};
+            for (int c = 0; c < 3; ++c) { P.f[c] = h.e(c); P.f[3 + c] = h.eT(c); }
+            P.f[6] = h.b(0); P.f[7] = h.b(1);
+            P.grid = h.j(2);
+            P.op.dtqm_e[0] = P.op.dtqm_e[1] = 0.5 * dt * qm;
+            P.op.dtqm = 0.5 * dt * qm;
+            P.op.wscale_dt = h.pg->charge * h.pg->common_weight * 0.5 * dt;
+            launch2(h, P, "fused[HE,HE,Hp3]{2,3}");
+        }
+    });
+    allreduce_sum(h.j(2), h.nd);
+    m2d_e_from_j(*h.maxwell, h.e(2), h.j(2), 3);
+}
+
+// strang_splitting! with the point-wise operators fused (same trajectory up to rounding):
+//   first step      HB ; [b -= dt/2 curl e] ; fused{HE,Hp3} ; Hp2 Hp1 Hp2 Hp3
+//   between steps   eT = e ; b -= dt/2 curl e ; HB ; HB ; b -= dt/2 curl e ; fused{HE(eT),HE,Hp3} ; Hp2 Hp1 Hp2 Hp3
+//   after the last  HE ; HB
+// (compute_b_from_e! of a HE only reads e, which the kick reads too, and writes b, which the kick does not read)
+static void strang2d_fused(Splitting2D &h, double dt, int64_t steps)
+{
+    const Maxwell2D &m = *h.maxwell;
+    double *b[3] = {h.b(0), h.b(1), h.b(2)};
+    const double *e[3] = {h.e(0), h.e(1), h.e(2)};
+    for (int64_t s = 0; s < steps; ++s) {
+        if (h.sort_interval > 0 && h.steps_done % h.sort_interval == 0) pg_sort_2d(*h.pg, *h.maxwell);
+        if (s == 0) {
+            hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);
+            m2d_b_from_e(m, b, 0.5 * dt, e);
+            fused_he_hp3(h, dt, 1);
+        } else {
+            GP_CUDA(cudaMemcpyAsync(h.eT(0), h.e(0), 3 * h.nd * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
+            m2d_b_from_e(m, b, 0.5 * dt, e);              // trailing HE of step s-1, field part
+            hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);     // trailing HB of step s-1
+            hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);     // leading HB of step s
+            m2d_b_from_e(m, b, 0.5 * dt, e);              // leading HE of step s, field part
+            fused_he_hp3(h, dt, 2);
+        }
+        hs2d_operator(h, GEMPIC_OP_HP2, 0.5 * dt);
+        hs2d_operator(h, GEMPIC_OP_HP1, dt);
+        hs2d_operator(h, GEMPIC_OP_HP2, 0.5 * dt);
+        hs2d_operator(h, GEMPIC_OP_HP3, 0.5 * dt);
+        h.steps_done++;
+    }
+    hs2d_operator(h, GEMPIC_OP_HE, 0.5 * dt);
+    hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);
+}
+
 void hs2d_strang(Splitting2D &h, double dt, int64_t steps)
 {
+    if (steps <= 0) return;
+    if (h.fuse) {
+        strang2d_fused(h, dt, steps);
+        return;
+    }
     for (int64_t s = 0; s < steps; ++s) {
         if (h.sort_interval > 0 && h.steps_done % h.sort_interval == 0) pg_sort_2d(*h.pg, *h.maxwell);
         hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);
@@ -771,7 +937,7 @@ int gempic_hs2d_create(gempic_handle maxwell2d, gempic_handle pgh, gempic_handle
     GP_REQUIRE(h->maxwell->nx >= 2 * kR2 + 2 && h->maxwell->ny >= 2 * kR2 + 2, GEMPIC_EINVAL,
                "HamiltonianSplitting{2,3} needs at least %d cells per direction", 2 * kR2 + 2);
     h->nd = (size_t)h->maxwell->nx * h->maxwell->ny;
-    h->fields.alloc(10 * h->nd + 16);
+    h->fields.alloc(13 * h->nd + 16);
     h->fields.zero(ctx().stream);
     *out = register_object(std::move(h));
     GP_API_END
@@ -862,6 +1028,14 @@ int gempic_hs2d_set_sort_interval(gempic_handle hs, int interval)
     GP_API_END
 }
 
+/* 1 (default): fused particle passes inside strang_splitting ([HE,Hp3] and the cross-step HE fold); 0: one pass per operator */
+int gempic_hs2d_set_fusion(gempic_handle hs, int fuse)
+{
+    GP_API_BEGIN
+    get<Splitting2D>(hs, "HamiltonianSplitting{2,3}")->fuse = fuse ? 1 : 0;
+    GP_API_END
+}
+
 /* rho[nx*ny] = add_charge! of all particles (degree p x p, get_charge weights), all-reduced over ranks */
 int gempic_hs2d_charge_density(gempic_handle hs, double *rho)
 {
@@ -882,7 +1056,7 @@ int gempic_hs2d_moments(gempic_handle hs, double *out4)
     require_init();
     Splitting2D *h = get<Splitting2D>(hs, "HamiltonianSplitting{2,3}");
     GP_REQUIRE(out4, GEMPIC_EINVAL, "null buffer");
-    double *d = h->fields.p + 10 * h->nd;
+    double *d = h->fields.p + 13 * h->nd;
     hs2d_moments(*h, d);
     d2h(out4, d, 4);
     GP_API_END

@@ -166,7 +166,8 @@ struct Splitting2D : Object {
     Maxwell2D *maxwell;
     ParticleGroup *pg;
     size_t nd = 0;             // nx * ny
-    DevBuf<double> fields;     // e1 e2 e3 b1 b2 b3 j1 j2 j3 rho (10 * nd) + 16 scalars
+    DevBuf<double> fields;     // e1 e2 e3 b1 b2 b3 j1 j2 j3 rho e1T e2T e3T (13 * nd) + 16 scalars
+    int fuse = 1;              // fused [HE,Hp3] pass and cross-step HE fold inside strang_splitting
     PartialScratch scratch;
     int sort_interval = 1;     // cell-sort every k Strang steps (0: never)
     int64_t steps_done = 0;
@@ -174,6 +175,7 @@ struct Splitting2D : Object {
     double *e(int c) { return fields.p + (size_t)c * nd; }
     double *b(int c) { return fields.p + (size_t)(3 + c) * nd; }
     double *j(int c) { return fields.p + (size_t)(6 + c) * nd; }
+    double *eT(int c) { return fields.p + (size_t)(10 + c) * nd; }
 };
 void hs2d_operator(Splitting2D &h, int op, double dt);
 void hs2d_strang(Splitting2D &h, double dt, int64_t steps);

@@ -223,6 +223,8 @@ int gempic_hs2d_strang_splitting_host(gempic_handle hs, double dt, int64_t numbe
                                       double *e3, double *b1, double *b2, double *b3);
 /* cell-sort the particles every `interval` Strang steps (0: never; default 1) */
 int gempic_hs2d_set_sort_interval(gempic_handle hs, int interval);
+/* 1 (default): fused [HE,Hp3] pass and cross-step HE fold inside strang_splitting; 0: one pass per operator */
+int gempic_hs2d_set_fusion(gempic_handle hs, int fuse);
 /* add_charge! of all particles onto the degree p x p dofs (get_charge weights), summed over ranks */
 int gempic_hs2d_charge_density(gempic_handle hs, double *rho);
 /* out[4] = sum_p w |v|^2, sum_p w v1, sum_p w v2, sum_p w v3, summed over ranks (diagnostics.jl:197-211) */

@@ -116,6 +116,18 @@ def test_strang_resident_sorted_matches_oracle(gp):
     assert np.all(np.diff(cell) >= 0)
 
 
+@pytest.mark.parametrize("fuse", [False, True])
+def test_strang_fused_and_unfused_match_oracle(gp, fuse):
+    """strang_splitting!(h, dt, 4) in one call (the fused path folds the trailing HE into the next step's pass),
+    particle order kept"""
+    ho, hg = build(gp, 12_000, 16, 12, 3, seed=31, resident=True)
+    hg.set_fusion(fuse)
+    ho.strang_splitting(0.05, 4)
+    hg.strang_splitting(0.05, 4)
+    hg.sync_fields()
+    check(ho, hg, BOX, tol=1e-10, what=f"strang fuse={fuse}")
+
+
 def test_invariants_at_scale(gp):
     """2e6 particles on 64x64, degree 3 (the BASELINE config 5 grid): Gauss law conserved to round-off,
     total charge exact, energy drift O(dt^2)"""
