@@ -39,6 +39,16 @@ __device__ __forceinline__ double gather_h(const double *__restrict__ field, int
     return v;
 }
 
+// sum_k field[k * S] * b[k]  (field points at the first dof of the stencil, copy stride S)
+template <int D, int S>
+__device__ __forceinline__ double gather_s(const double *__restrict__ field, const double (&b)[D + 1])
+{
+    double v = field[0] * b[0];
+#pragma unroll
+    for (int k = 1; k <= D; ++k) v = fma(field[k * S], b[k], v);
+    return v;
+}
+
 // grid[g0+k] += ws * N_k   with ws = marker charge * scaling   (add_charge!, pmc1d.jl:261-280)
 template <int D, bool LP>
 __device__ __forceinline__ void deposit_h(const Acc<LP> &acc, int slot0, const double (&b)[D + 1], double ws)
@@ -232,16 +242,6 @@ __device__ __forceinline__ int wrap_near(int g, int n)
 {
     g = g < 0 ? g + n : g;
     return g >= n ? g - n : g;
-}
-
-// sum_k field[k * S] * b[k]  (field points at the first dof of the stencil, copy stride S)
-template <int D, int S>
-__device__ __forceinline__ double gather_s(const double *__restrict__ field, const double (&b)[D + 1])
-{
-    double v = field[0] * b[0];
-#pragma unroll
-    for (int k = 1; k <= D; ++k) v = fma(field[k * S], b[k], v);
-    return v;
 }
 
 template <int D0, int D1, int NHE>
@@ -611,6 +611,11 @@ struct OpBorisStep {
     static constexpr int READ = ROW_X | ROW_V1 | ROW_V2 | ROW_W, WRITE = ROW_X | ROW_V1 | ROW_V2;
     static constexpr int NF = 3, NG = 2, NS = 0;
     static constexpr bool DEPOSIT = true;
+    // like the fused Strang pass this one is bound by the shared-memory pipe: conflict-free gathers from 16
+    // lane-interleaved field copies, one block of 8 warps per SM
+    static constexpr int THREADS = 256;
+    static constexpr int FIELD_COPIES = 16;
+    static constexpr int FC = FIELD_COPIES;
     struct Params { double dt, half_dtqm, qmdt, wscale0, wscale1; };
     template <bool LP>
     static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpBorisStep> &P, const double *sf, const Acc<LP> &acc)
@@ -622,9 +627,9 @@ struct OpBorisStep {
         double b1[D1 + 1], b0[D0 + 1];
         basis_pp<D1>(ps.t, b1);
         basis_pp<D0>(ps.t, b0);
-        const double e1 = gather_h<D1>(sf, g1, b1);
-        const double e2 = gather_h<D0>(sf + nh, g0, b0);
-        const double bf = gather_h<D1>(sf + 2 * nh, g1, b1);
+        const double e1 = gather_s<D1, FC>(sf + (size_t)g1 * FC, b1);
+        const double e2 = gather_s<D0, FC>(sf + (size_t)(nh + g0) * FC, b0);
+        const double bf = gather_s<D1, FC>(sf + (size_t)(2 * nh + g1) * FC, b1);
         p.v1 = fma(P.op.half_dtqm, e1, p.v1);
         p.v2 = fma(P.op.half_dtqm, e2, p.v2);
         boris_rotate(p, bf, P.op.qmdt);
