@@ -45,7 +45,7 @@ int gempic_pg_upload(gempic_handle h, const double *aos)
 {
     GP_API_BEGIN
     require_init();
-    ParticleGroup *pg = get<ParticleGroup>(h, "ParticleGroup");
+    ParticleGroup *pg = get_pg(h);
     GP_REQUIRE(aos || pg->n == 0, GEMPIC_EINVAL, "null particle array");
     if (pg->n) pg_upload(*pg, aos);
     GP_API_END
@@ -55,7 +55,7 @@ int gempic_pg_download(gempic_handle h, double *aos)
 {
     GP_API_BEGIN
     require_init();
-    ParticleGroup *pg = get<ParticleGroup>(h, "ParticleGroup");
+    ParticleGroup *pg = get_pg(h);
     GP_REQUIRE(aos || pg->n == 0, GEMPIC_EINVAL, "null particle array");
     if (pg->n) pg_download(*pg, aos);
     GP_API_END
@@ -65,7 +65,7 @@ int gempic_pg_set_row_device(gempic_handle h, int row, const double *dev_src)
 {
     GP_API_BEGIN
     require_init();
-    ParticleGroup *pg = get<ParticleGroup>(h, "ParticleGroup");
+    ParticleGroup *pg = get_pg(h);
     GP_REQUIRE(row >= 0 && row < pg->rows() && dev_src, GEMPIC_EINVAL, "bad row %d", row);
     GP_CUDA(cudaMemcpyAsync(pg->row(row), dev_src, sizeof(double) * pg->n, cudaMemcpyDeviceToDevice, ctx().stream));
     GP_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -76,7 +76,7 @@ int gempic_pg_get_row_device(gempic_handle h, int row, double *dev_dst)
 {
     GP_API_BEGIN
     require_init();
-    ParticleGroup *pg = get<ParticleGroup>(h, "ParticleGroup");
+    ParticleGroup *pg = get_pg(h);
     GP_REQUIRE(row >= 0 && row < pg->rows() && dev_dst, GEMPIC_EINVAL, "bad row %d", row);
     GP_CUDA(cudaMemcpyAsync(dev_dst, pg->row(row), sizeof(double) * pg->n, cudaMemcpyDeviceToDevice, ctx().stream));
     GP_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -87,7 +87,7 @@ int gempic_pg_row_ptr(gempic_handle h, int row, double **dev_ptr)
 {
     GP_API_BEGIN
     require_init();
-    ParticleGroup *pg = get<ParticleGroup>(h, "ParticleGroup");
+    ParticleGroup *pg = get_pg(h);
     GP_REQUIRE(row >= 0 && row < pg->rows() && dev_ptr, GEMPIC_EINVAL, "bad row %d", row);
     *dev_ptr = pg->row(row);
     GP_API_END
@@ -97,7 +97,7 @@ int gempic_pg_info(gempic_handle h, int *D, int *V, int *n_weights, int64_t *n_p
                    double *common_weight)
 {
     GP_API_BEGIN
-    ParticleGroup *pg = get<ParticleGroup>(h, "ParticleGroup");
+    ParticleGroup *pg = get_pg(h);
     if (D) *D = pg->D;
     if (V) *V = pg->V;
     if (n_weights) *n_weights = pg->W;
@@ -112,7 +112,7 @@ int gempic_pg_sort(gempic_handle h, gempic_handle pmc)
 {
     GP_API_BEGIN
     require_init();
-    ParticleGroup *pg = get<ParticleGroup>(h, "ParticleGroup");
+    ParticleGroup *pg = get_pg(h);
     GP_REQUIRE(pg->D == 1, GEMPIC_EINVAL, "cell sort is implemented for D = 1 particle groups");
     Pmc1D *p = get<Pmc1D>(pmc, "ParticleMeshCoupling1D");
     pg_sort_1d(*pg, *p);
@@ -124,7 +124,7 @@ int gempic_pg_sample(gempic_handle h, int kind, double xmin, double L, double al
 {
     GP_API_BEGIN
     require_init();
-    ParticleGroup *pg = get<ParticleGroup>(h, "ParticleGroup");
+    ParticleGroup *pg = get_pg(h);
     GP_REQUIRE(L > 0.0, GEMPIC_EINVAL, "domain length must be positive");
     pg_sample(*pg, kind, xmin, L, alpha, k, sigma, seed, first_index);
     GP_API_END
@@ -247,7 +247,7 @@ int gempic_pmc1d_add_charge_pg(gempic_handle pmc, gempic_handle pgh, double *rho
     GP_API_BEGIN
     require_init();
     Pmc1D *p = get<Pmc1D>(pmc, "ParticleMeshCoupling1D");
-    ParticleGroup *pg = get<ParticleGroup>(pgh, "ParticleGroup");
+    ParticleGroup *pg = get_pg(pgh);
     GP_REQUIRE(pg->D == 1, GEMPIC_EASSERT, "ParticleMeshCoupling1D needs a ParticleGroup{1,V}");
     GP_REQUIRE(rho, GEMPIC_EINVAL, "null rho");
     pmc1d_add_charge_dev(*p, pg->row(0), pg->row(pg->D + pg->V), pg->n, pg->charge, pg->common_weight, p->grid_tmp.p);
@@ -261,7 +261,7 @@ int gempic_pmc1d_evaluate_pg(gempic_handle pmc, gempic_handle pgh, const double 
     GP_API_BEGIN
     require_init();
     Pmc1D *p = get<Pmc1D>(pmc, "ParticleMeshCoupling1D");
-    ParticleGroup *pg = get<ParticleGroup>(pgh, "ParticleGroup");
+    ParticleGroup *pg = get_pg(pgh);
     GP_REQUIRE(pg->D == 1, GEMPIC_EASSERT, "ParticleMeshCoupling1D needs a ParticleGroup{1,V}");
     GP_REQUIRE(field && (out || pg->n == 0), GEMPIC_EINVAL, "null buffer");
     if (pg->n == 0) return GEMPIC_OK;
@@ -433,7 +433,7 @@ int gempic_hs_create(int D, int V, gempic_handle maxwell, gempic_handle pmc0, ge
     h->maxwell = get<Maxwell1D>(maxwell, "Maxwell1DFEM");
     h->ks0 = get<Pmc1D>(pmc0, "ParticleMeshCoupling1D");
     h->ks1 = get<Pmc1D>(pmc1, "ParticleMeshCoupling1D");
-    h->pg = get<ParticleGroup>(pgh, "ParticleGroup");
+    h->pg = get_pg(pgh);
     GP_REQUIRE(D == 1 && (V == 1 || V == 2), GEMPIC_EINVAL, "HamiltonianSplitting{%d,%d} is not defined by the reference", D, V);
     GP_REQUIRE(h->pg->D == D && h->pg->V == V, GEMPIC_EASSERT, "dims == particle_group.dims (hamiltonian_splitting.jl:47)");
     GP_REQUIRE(h->ks0->n_grid == h->ks1->n_grid, GEMPIC_EASSERT,
@@ -442,6 +442,7 @@ int gempic_hs_create(int D, int V, gempic_handle maxwell, gempic_handle pmc0, ge
     GP_REQUIRE(h->ks0->xmin == h->ks1->xmin && h->ks0->xmax == h->ks1->xmax, GEMPIC_EINVAL,
                "both kernel smoothers must live on the same mesh");
     h->D = D; h->V = V; h->n = h->ks0->n_grid;
+    h->pg_handle = pgh;
     h->fields.alloc((size_t)10 * h->n);
     h->fields.zero(ctx().stream);
     *out = register_object(std::move(h));
@@ -451,6 +452,12 @@ int gempic_hs_create(int D, int V, gempic_handle maxwell, gempic_handle pmc0, ge
 int gempic_hs_destroy(gempic_handle hs)
 {
     GP_API_BEGIN
+    Splitting *h = get<Splitting>(hs, "HamiltonianSplitting");
+    try {   // a deferred HE kick must not be lost; the particle group may already be gone
+        ParticleGroup *pg = get<ParticleGroup>(h->pg_handle, "ParticleGroup");
+        if (pg->pending == h) pg_sync(*pg);
+    } catch (const Fail &) {
+    }
     destroy(hs, Kind::Splitting, "HamiltonianSplitting");
     GP_API_END
 }
@@ -537,7 +544,7 @@ int gempic_boris_create(gempic_handle maxwell, gempic_handle pmc0, gempic_handle
     s->maxwell = get<Maxwell1D>(maxwell, "Maxwell1DFEM");
     s->ks0 = get<Pmc1D>(pmc0, "ParticleMeshCoupling1D");
     s->ks1 = get<Pmc1D>(pmc1, "ParticleMeshCoupling1D");
-    s->pg = get<ParticleGroup>(pgh, "ParticleGroup");
+    s->pg = get_pg(pgh);
     GP_REQUIRE(s->pg->D == 1 && s->pg->V == 2, GEMPIC_EASSERT, "HamiltonianSplittingBoris needs a ParticleGroup{1,2}");
     GP_REQUIRE(s->ks0->n_grid == s->ks1->n_grid && s->ks0->n_grid == s->maxwell->n, GEMPIC_EASSERT, "n_dofs mismatch");
     GP_REQUIRE(s->ks0->xmin == s->ks1->xmin && s->ks0->xmax == s->ks1->xmax, GEMPIC_EINVAL,
@@ -561,6 +568,7 @@ int gempic_boris_set_fields(gempic_handle bs, const double *e1, const double *e2
     GP_API_BEGIN
     require_init();
     Boris *s = get<Boris>(bs, "HamiltonianSplittingBoris");
+    pg_sync(*s->pg);
     if (e1) h2d(s->f(GEMPIC_F_E1), e1, s->n);
     if (e2) h2d(s->f(GEMPIC_F_E2), e2, s->n);
     if (b) h2d(s->f(GEMPIC_F_B), b, s->n);
@@ -572,6 +580,7 @@ int gempic_boris_get_field(gempic_handle bs, int which, double *out)
     GP_API_BEGIN
     require_init();
     Boris *s = get<Boris>(bs, "HamiltonianSplittingBoris");
+    pg_sync(*s->pg);
     GP_REQUIRE(which >= 0 && which <= GEMPIC_F_B_MID && out, GEMPIC_EINVAL, "bad field selector %d", which);
     d2h(out, s->f(which), s->n);
     GP_API_END
@@ -583,6 +592,7 @@ int gempic_boris_get_field(gempic_handle bs, int which, double *out)
         GP_API_BEGIN                                                   \
         require_init();                                                \
         Boris *s = get<Boris>(bs, "HamiltonianSplittingBoris");        \
+        pg_sync(*s->pg);                                               \
         FN(*s, dt);                                                    \
         GP_API_END                                                     \
     }
@@ -596,6 +606,7 @@ int gempic_boris_strang_splitting(gempic_handle bs, double dt, int64_t number_st
     GP_API_BEGIN
     require_init();
     Boris *s = get<Boris>(bs, "HamiltonianSplittingBoris");
+    pg_sync(*s->pg);
     GP_REQUIRE(number_steps >= 0, GEMPIC_EINVAL, "negative step count");
     boris_strang(*s, dt, number_steps);
     GP_API_END
@@ -633,7 +644,7 @@ int gempic_solve_poisson(gempic_handle pgh, gempic_handle pmc0, gempic_handle mh
 {
     GP_API_BEGIN
     require_init();
-    ParticleGroup *pg = get<ParticleGroup>(pgh, "ParticleGroup");
+    ParticleGroup *pg = get_pg(pgh);
     Pmc1D *p = get<Pmc1D>(pmc0, "ParticleMeshCoupling1D");
     Maxwell1D *m = get<Maxwell1D>(mh, "Maxwell1DFEM");
     GP_REQUIRE(pg->D == 1, GEMPIC_EASSERT, "solve_poisson! is 1D");
@@ -654,7 +665,7 @@ int gempic_diag_write_step(gempic_handle pgh, gempic_handle mh, gempic_handle pm
 {
     GP_API_BEGIN
     require_init();
-    ParticleGroup *pg = get<ParticleGroup>(pgh, "ParticleGroup");
+    ParticleGroup *pg = get_pg(pgh);
     Maxwell1D *m = get<Maxwell1D>(mh, "Maxwell1DFEM");
     Pmc1D *ks0 = get<Pmc1D>(pmc0, "ParticleMeshCoupling1D");
     Pmc1D *ks1 = get<Pmc1D>(pmc1, "ParticleMeshCoupling1D");

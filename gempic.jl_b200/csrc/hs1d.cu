@@ -93,7 +93,7 @@ static void op_Hp1(Splitting &h, double dt, bool with_rho)
 // fused particle pass [HE x n_he, Hp2(dt/2), Hp1(dt), Hp2(dt/2)] + the three field solves.
 // n_he = 1: fields e1,e2 = current.  n_he = 2: the first kick reads the snapshot (e1T, e2T)
 // taken before the trailing HE's field update of the previous step.
-static void fused_pass(Splitting &h, double dt, int n_he)
+static void fused_pass(Splitting &h, double dt, int n_he, double dt_T)
 {
     const double qm = h.pg->q_over_m;
     GP_DISPATCH_DEGREES(h.ks0->degree, h.ks1->degree, {
@@ -117,7 +117,8 @@ static void fused_pass(Splitting &h, double dt, int n_he)
             P.fields[2] = h.e1();
             P.fields[3] = h.e2();
             P.fields[4] = h.b();
-            P.op.dtqm_e[0] = P.op.dtqm_e[1] = 0.5 * dt * qm;
+            P.op.dtqm_e[0] = 0.5 * dt_T * qm;   // trailing HE of the previous step (snapshot fields)
+            P.op.dtqm_e[1] = 0.5 * dt * qm;
             P.op.dtqm_p2 = 0.5 * dt * qm;
             typename OpHp1<D0, D1, false>::Params hp;
             set_hp1_params<OpHp1<D0, D1, false>>(h, dt, hp);
@@ -159,22 +160,43 @@ static bool fused_fits(Splitting &h)
 static void strang_fused(Splitting &h, double dt, int64_t steps)
 {
     const Maxwell1D &m = *h.maxwell;
+    ParticleGroup &pg = *h.pg;
+    if (pg.pending && pg.pending != &h) pg_sync(pg);
     for (int64_t s = 0; s < steps; ++s) {
-        if (s == 0) {
+        if (s == 0 && !pg.pending) {
             op_HB(h, 0.5 * dt);
             field_b_from_e(m, h.b(), 0.5 * dt, h.e2());
-            fused_pass(h, dt, 1);
+            fused_pass(h, dt, 1, dt);
+        } else if (s == 0) {
+            // the previous call left its trailing HE kick pending (fields already advanced, snapshot in e1T|e2T)
+            pg.pending = nullptr;
+            op_HB(h, 0.5 * dt);
+            field_b_from_e(m, h.b(), 0.5 * dt, h.e2());
+            fused_pass(h, dt, 2, h.pending_dt);
         } else {
             field_copy(h.e1T(), h.e1(), 2 * h.n);            // e1T|e2T <- e1|e2 (adjacent)
             field_b_from_e(m, h.b(), 0.5 * dt, h.e2());      // trailing HE of step s-1, field part
             op_HB(h, 0.5 * dt);                              // trailing HB of step s-1
             op_HB(h, 0.5 * dt);                              // leading HB of step s
             field_b_from_e(m, h.b(), 0.5 * dt, h.e2());      // leading HE of step s, field part
-            fused_pass(h, dt, 2);
+            fused_pass(h, dt, 2, dt);
         }
     }
-    op_HE(h, 0.5 * dt);
+    // trailing HE + HB: the fields are advanced now; the particle kick (which only reads the snapshot) is deferred
+    // to the next call of this splitting, or applied by pg_sync() as soon as anybody else touches the particles
+    field_copy(h.e1T(), h.e1(), 2 * h.n);
+    field_b_from_e(m, h.b(), 0.5 * dt, h.e2());
     op_HB(h, 0.5 * dt);
+    h.pending_dt = dt;
+    pg.pending = &h;
+}
+
+void pg_sync(ParticleGroup &pg)
+{
+    Splitting *h = pg.pending;
+    if (!h) return;
+    pg.pending = nullptr;
+    op_HE_particles(*h, 0.5 * h->pending_dt, h->e1T(), h->e2T());
 }
 
 // ---- {1,1} ----------------------------------------------------------------------------
@@ -204,6 +226,7 @@ static void op_Hp111(Splitting &h, double dt)
 
 void hs_operator(Splitting &h, int op, double dt, bool inside_strang)
 {
+    pg_sync(*h.pg);
     if (h.V == 2) {
         switch (op) {
         case GEMPIC_OP_HP1: op_Hp1(h, dt, !inside_strang); break;
@@ -245,6 +268,7 @@ void hs_strang(Splitting &h, double dt, int64_t steps)
         strang_fused(h, dt, steps);
         return;
     }
+    pg_sync(*h.pg);
     for (int64_t s = 0; s < steps; ++s) strang_step(h, dt);
 }
 

@@ -930,7 +930,7 @@ int gempic_hs2d_create(gempic_handle maxwell2d, gempic_handle pgh, gempic_handle
     GP_REQUIRE(out, GEMPIC_EINVAL, "null output handle");
     auto h = std::make_unique<Splitting2D>();
     h->maxwell = get<Maxwell2D>(maxwell2d, "TwoDMaxwell");
-    h->pg = get<ParticleGroup>(pgh, "ParticleGroup");
+    h->pg = get_pg(pgh);
     GP_REQUIRE(h->pg->D == 2 && h->pg->V == 3, GEMPIC_EASSERT, "dims == (2, 3) (hamiltonian_splitting.jl:47)");
     GP_REQUIRE(h->pg->W >= 1, GEMPIC_EASSERT, "particle group needs a weight row");
     GP_REQUIRE(h->maxwell->s_deg_0 >= 1, GEMPIC_EINVAL, "degree");
@@ -1066,7 +1066,7 @@ int gempic_pg_sort2d(gempic_handle pgh, gempic_handle maxwell2d)
 {
     GP_API_BEGIN
     require_init();
-    ParticleGroup *pg = get<ParticleGroup>(pgh, "ParticleGroup");
+    ParticleGroup *pg = get_pg(pgh);
     GP_REQUIRE(pg->D == 2, GEMPIC_EINVAL, "2D cell sort needs a D = 2 particle group");
     pg_sort_2d(*pg, *get<Maxwell2D>(maxwell2d, "TwoDMaxwell"));
     GP_API_END

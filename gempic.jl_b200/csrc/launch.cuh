@@ -32,7 +32,7 @@ inline LaunchInfo plan_pass(const PassParams<Op> &P)
 {
     LaunchInfo L;
     constexpr int kNW = op_threads<Op>::value / 32;
-    const size_t field_bytes = (size_t)Op::NF * (P.m.n + op_halo<Op>::value) * op_field_copies<Op>::value * sizeof(double);
+    const size_t field_bytes = (size_t)Op::NF * (P.m.n + op_field_halo<Op>::value) * op_field_copies<Op>::value * sizeof(double);
     if (!Op::DEPOSIT) {
         L.lane_private = true;
         L.smem = field_bytes;

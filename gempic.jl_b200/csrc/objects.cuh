@@ -7,8 +7,13 @@ namespace gempic {
 
 // ParticleGroup{D,V} (src/particle_group.jl:15-46): device SoA, one fp64 row per
 // coordinate, rows ordered x1..xD, v1..vV, w1..wW like the rows of the reference array.
+struct Splitting;
 struct ParticleGroup : Object {
     static constexpr Kind kKind = Kind::ParticleGroup;
+    // A fused strang_splitting! call may leave its trailing operatorHE kick pending (hs1d.cu): the velocities lag
+    // by that kick until the owner's next call folds it into its first pass, or pg_sync() applies it because
+    // somebody else is about to look at the particles.
+    Splitting *pending = nullptr;
     int D, V, W;
     int64_t n;
     double charge, mass, common_weight, q_over_m;
@@ -124,6 +129,8 @@ struct Splitting : Object {
     DevBuf<double> fields;  // e1, e2, b, j1, j2, acc(3n), e1T, e2T   (10 * n)
     PartialScratch scratch;
     int fuse = 0;
+    double pending_dt = 0.0;       // dt of the deferred trailing HE kick (ParticleGroup::pending == this)
+    gempic_handle pg_handle = 0;
     // CUDA graph of one Strang step, keyed by dt
     cudaGraphExec_t graph = nullptr;
     double graph_dt = 0.0;
@@ -180,6 +187,15 @@ struct Splitting2D : Object {
 void hs2d_operator(Splitting2D &h, int op, double dt);
 void hs2d_strang(Splitting2D &h, double dt, int64_t steps);
 void pg_sort_2d(ParticleGroup &pg, const Maxwell2D &m);
+
+// applies a deferred trailing HE kick, if any (hs1d.cu); every entry point that reads or moves particles calls it
+void pg_sync(ParticleGroup &pg);
+inline ParticleGroup *get_pg(gempic_handle h)
+{
+    ParticleGroup *pg = get<ParticleGroup>(h, "ParticleGroup");
+    pg_sync(*pg);
+    return pg;
+}
 
 // operator implementations (hs1d.cu / boris.cu)
 void hs_operator(Splitting &h, int op, double dt, bool inside_strang);

@@ -63,6 +63,10 @@ struct op_halo { static constexpr int value = kMaxDegree + 1; };
 template <class Op>
 struct op_halo<Op, std::void_t<decltype(Op::HALO)>> { static constexpr int value = Op::HALO; };
 template <class Op, class = void>
+struct op_field_halo { static constexpr int value = op_halo<Op>::value; };   // halo of the staged FIELD vectors
+template <class Op>
+struct op_field_halo<Op, std::void_t<decltype(Op::FIELD_HALO)>> { static constexpr int value = Op::FIELD_HALO; };
+template <class Op, class = void>
 struct op_field_copies { static constexpr int value = 1; };
 template <class Op>
 struct op_field_copies<Op, std::void_t<decltype(Op::FIELD_COPIES)>> { static constexpr int value = Op::FIELD_COPIES; };
@@ -165,11 +169,11 @@ template <class Op, bool LP>
 __global__ void __launch_bounds__(op_threads<Op>::value) k_pass(const __grid_constant__ PassParams<Op> P)
 {
     constexpr int kThreads = op_threads<Op>::value, kNW = kThreads / 32, kH = op_halo<Op>::value,
-                  kFC = op_field_copies<Op>::value;
+                  kFH = op_field_halo<Op>::value, kFC = op_field_copies<Op>::value;
     extern __shared__ double smem[];
     const int tid = threadIdx.x;
     const int n = P.m.n;
-    const int nh = n + kH;
+    const int nh = n + kH, nhf = n + kFH;
     // ---- stage the field dofs this op gathers from (with periodic halo) -------------------
     double *sfield = smem;
     if constexpr (op_has_stage<Op>::value) {
@@ -177,14 +181,14 @@ __global__ void __launch_bounds__(op_threads<Op>::value) k_pass(const __grid_con
     } else {
 #pragma unroll
         for (int f = 0; f < Op::NF; ++f)
-            for (int i = tid; i < nh; i += kThreads) {
+            for (int i = tid; i < nhf; i += kThreads) {
                 const double v = P.fields[f][i < n ? i : i - n];
 #pragma unroll
-                for (int c = 0; c < kFC; ++c) sfield[(size_t)(f * nh + i) * kFC + c] = v;
+                for (int c = 0; c < kFC; ++c) sfield[(size_t)(f * nhf + i) * kFC + c] = v;
             }
     }
     // ---- zero the block-private accumulators --------------------------------------------
-    double *sacc = smem + (size_t)Op::NF * nh * kFC;
+    double *sacc = smem + (size_t)Op::NF * nhf * kFC;
     const int slots = acc_slots<Op>(n);
     const int acc_words = Op::DEPOSIT ? (LP ? slots * 32 * kNW : slots * P.copies) : 0;
     for (int i = tid; i < acc_words; i += kThreads) sacc[i] = 0.0;

@@ -224,7 +224,7 @@ int gempic_pmc2d_add_charge_pg(gempic_handle pmc, gempic_handle pgh, double *rho
     GP_API_BEGIN
     require_init();
     Pmc2D *p = get<Pmc2D>(pmc, "ParticleMeshCoupling2D");
-    ParticleGroup *pg = get<ParticleGroup>(pgh, "ParticleGroup");
+    ParticleGroup *pg = get_pg(pgh);
     GP_REQUIRE(pg->D == 2, GEMPIC_EASSERT, "ParticleMeshCoupling2D needs a ParticleGroup{2,V}");
     GP_REQUIRE(rho, GEMPIC_EINVAL, "null rho");
     const size_t ng = (size_t)p->m.nx * p->m.ny;
@@ -241,7 +241,7 @@ int gempic_pmc2d_evaluate_pg(gempic_handle pmc, gempic_handle pgh, const double 
     GP_API_BEGIN
     require_init();
     Pmc2D *p = get<Pmc2D>(pmc, "ParticleMeshCoupling2D");
-    ParticleGroup *pg = get<ParticleGroup>(pgh, "ParticleGroup");
+    ParticleGroup *pg = get_pg(pgh);
     GP_REQUIRE(pg->D == 2, GEMPIC_EASSERT, "ParticleMeshCoupling2D needs a ParticleGroup{2,V}");
     GP_REQUIRE(field && out, GEMPIC_EINVAL, "null buffer");
     const size_t ng = (size_t)p->m.nx * p->m.ny;

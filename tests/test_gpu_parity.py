@@ -112,6 +112,44 @@ def test_strang_fused_equals_unfused_long_run(gp):
     assert abs(energy(sa) - energy(sb)) < 1e-7 * abs(energy(sa))
 
 
+def test_deferred_trailing_kick_is_invisible(orc, gp):
+    """the fused strang_splitting! defers its trailing HE particle kick to the next call (csrc/hs1d.cu, pg_sync): no
+    sequence of calls may observe the lag -- varying dt, single operators, diagnostics, a second splitting object on
+    the same particle group, particle downloads in between"""
+    n = 30_000
+    state = weibel_state(n, L_WEIBEL, seed=77)
+    so, sg = both(orc, gp, state, L_WEIBEL, nx=32)
+    so.init_fields(b_amp=1e-2, e2_amp=1e-3), sg.init_fields(b_amp=1e-2, e2_amp=1e-3)
+    ho, hg = so.splitting(), sg.splitting()
+    hg.set_fusion(True)
+    for dt in (0.05, 0.03, 0.07):                  # back-to-back calls: the kick rides in the next call's pass
+        ho.strang_splitting(dt, 1), hg.strang_splitting(dt, 1)
+        check_fields(so, sg, tol=1e-11)
+    assert particle_err(sg.particles(), so.particles(), L_WEIBEL) < 1e-11    # download applies the pending kick
+    ho.strang_splitting(0.05, 2), hg.strang_splitting(0.05, 2)
+    ho.operatorHp1(0.02), hg.operatorHp1(0.02)     # a single operator after a fused call
+    assert particle_err(sg.particles(), so.particles(), L_WEIBEL) < 1e-11
+    check_fields(so, sg, tol=1e-11)
+    ho.strang_splitting(0.05, 1), hg.strang_splitting(0.05, 1)
+    epo, epg, rho_o, rho_g = np.zeros(32), np.zeros(32), np.zeros(32), np.zeros(32)
+    orc.solve_poisson(epo, so.pg, so.ks0, so.mx, rho_o)
+    gp.solve_poisson(epg, sg.pg, sg.ks0, sg.mx, rho_g)
+    ref = orc.write_step(so.pg, so.mx, so.ks0, so.ks1, 0.1, 3, [so.e1, so.e2], so.b, [so.e1, so.e2], epo)
+    got = gp.write_step(gp.TimeHistoryDiagnostics(sg.pg, sg.mx, sg.ks0, sg.ks1), 0.1, 3, [sg.e1, sg.e2], sg.b, [sg.e1, sg.e2], epg)
+    assert abs(got[1] - ref[1]) < 1e-10 * abs(ref[1])                        # kinetic energy sees the kick
+    # a second splitting object on the same particles (other field arrays) must see fully kicked particles
+    ho.strang_splitting(0.05, 1), hg.strang_splitting(0.05, 1)
+    e1b, e2b, bb = so.e1.copy(), so.e2.copy(), so.b.copy()
+    e1c, e2c, bc = sg.e1.copy(), sg.e2.copy(), sg.b.copy()
+    ho2 = orc.HamiltonianSplitting(1, 2, so.mx, so.ks0, so.ks1, so.pg, [e1b, e2b], bb)
+    hg2 = gp.HamiltonianSplitting(1, 2, sg.mx, sg.ks0, sg.ks1, sg.pg, [e1c, e2c], bc)
+    hg2.set_fusion(True)
+    ho2.strang_splitting(0.04, 1), hg2.strang_splitting(0.04, 1)
+    ho.strang_splitting(0.05, 1), hg.strang_splitting(0.05, 1)               # and back to the first one
+    assert particle_err(sg.particles(), so.particles(), L_WEIBEL) < 1e-10
+    assert rel_err(e1c, e1b) < 1e-10 and rel_err(sg.e1, so.e1) < 1e-10 and rel_err(sg.b, so.b) < 1e-10
+
+
 def test_multicell_and_backward_crossings(orc, gp):
     # fast particles: several cells per step in both directions, x_new < 0 (trunc quirk, SURVEY Q1)
     n = 20_000
