@@ -12,7 +12,7 @@ A "step" is one strang_splitting!(h, dt, 1): five streaming particle passes
 
 value   device-resident path (fields stay on the GPU), CUDA events on the library stream.
 e2e     the reference-facing call with HOST field buffers: every step copies e1,e2,b host->device
-        and e1,e2,b,j1,j2 device->host inside the timed region (gempic_hs_strang_splitting_host),
+        and e1,e2,b device->host inside the timed region (gempic_hs_strang_splitting_host),
         exactly what the Julia shim does for the aliased e_dofs/b_dofs arrays.
 roofline  dominant kernel = operatorHp1 pass: 48 algorithmic B/particle
         over its mean device time, measured with CUDA events inside the timed region.
@@ -65,7 +65,8 @@ BYTES2 = {"fused[HE,Hp3]{2,3}": 72, "fused[HE,HE,Hp3]{2,3}": 72, "operatorHE{2,3
           "strang_step": 2 * 64 + 2 * 64 + 3 * 72}
 # algorithmic DRAM bytes per particle of each pass (fp64 SoA rows x, v1, v2, w; SURVEY section 8d / DESIGN.md)
 BYTES = {"operatorHE": 40, "operatorHp2": 40, "operatorHp1": 48, "strang_step": 208,
-         "fused[HE,Hp2,Hp1,Hp2]": 56, "fused[HE,HE,Hp2,Hp1,Hp2]": 56, "boris_step": 56, "boris_strang_step": 56}
+         "fused[HE,Hp2,Hp1,Hp2]": 56, "fused[HE,HE,Hp2,Hp1,Hp2]": 56, "boris_step": 56, "boris_strang_step": 56,
+         "operatorHE+j2": 48, "j2 deposit": 24}
 
 
 def ncu_traffic(tag):
@@ -541,9 +542,9 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, n_local),
             "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 3 * NX * 8,
-                    "d2h_bytes_per_step": 5 * NX * 8, "steps": e2e_steps,
+                    "d2h_bytes_per_step": 3 * NX * 8, "steps": e2e_steps,
                     "what": ("gempic_boris_strang_splitting_host" if boris else "gempic_hs_strang_splitting_host") +
-                            ": host e1,e2,b in, e1,e2,b(,j1,j2) out, synchronous"},
+                            ": host e1,e2,b in, e1,e2,b out, synchronous"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }
         emit(line)

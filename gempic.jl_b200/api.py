@@ -490,19 +490,26 @@ class HamiltonianSplitting(_Handle):
         n = kernel_smoother_0.n_dofs
         self.e_dofs = [_check_alias(e_dofs[0], n), _check_alias(e_dofs[1], n)]
         self.b_dofs = _check_alias(b_dofs, n)
-        self.j_dofs = [np.zeros(n), np.zeros(n)]
+        self._j = [np.zeros(n), np.zeros(n)]
         self.Lx, self.x_min = maxwell_solver.Lx, maxwell_solver.xmin
         self.delta_x = self.Lx / n
         self.resident = resident
         if resident:
             self.upload_fields()
 
+    @property
+    def j_dofs(self):
+        """`j_dofs` of the reference struct (hamiltonian_splitting.jl:51): scratch owned by the splitting object, which
+        no caller of the reference reads.  It lives on the device and is read back on access; after a fused
+        strang_splitting! that access rebuilds j_dofs[2] from the particles (csrc/hs1d.cu, materialise_j2)."""
+        check(_L().gempic_hs_get_fields(self._h, None, None, None, dptr(self._j[0]), dptr(self._j[1])))
+        return self._j
+
     def upload_fields(self):
         check(_L().gempic_hs_set_fields(self._h, dptr(self.e_dofs[0]), dptr(self.e_dofs[1]), dptr(self.b_dofs)))
 
     def sync_fields(self):
-        check(_L().gempic_hs_get_fields(self._h, dptr(self.e_dofs[0]), dptr(self.e_dofs[1]), dptr(self.b_dofs),
-                                        dptr(self.j_dofs[0]), dptr(self.j_dofs[1])))
+        check(_L().gempic_hs_get_fields(self._h, dptr(self.e_dofs[0]), dptr(self.e_dofs[1]), dptr(self.b_dofs), None, None))
 
     def set_fusion(self, fuse: bool):
         check(_L().gempic_hs_set_fusion(self._h, C.c_int(1 if fuse else 0)))
@@ -514,7 +521,7 @@ class HamiltonianSplitting(_Handle):
             check(_L().gempic_hs_operator(self._h, C.c_int(op), _f(dt)))
         else:
             check(_L().gempic_hs_operator_host(self._h, C.c_int(op), _f(dt), dptr(self.e_dofs[0]), dptr(self.e_dofs[1]),
-                                               dptr(self.b_dofs), dptr(self.j_dofs[0]), dptr(self.j_dofs[1])))
+                                               dptr(self.b_dofs), None, None))
         pg._touched()
 
     def operatorHp1(self, dt):
@@ -536,8 +543,7 @@ class HamiltonianSplitting(_Handle):
             check(_L().gempic_hs_strang_splitting(self._h, _f(dt), C.c_int64(number_steps)))
         else:
             check(_L().gempic_hs_strang_splitting_host(self._h, _f(dt), C.c_int64(number_steps), dptr(self.e_dofs[0]),
-                                                       dptr(self.e_dofs[1]), dptr(self.b_dofs), dptr(self.j_dofs[0]),
-                                                       dptr(self.j_dofs[1])))
+                                                       dptr(self.e_dofs[1]), dptr(self.b_dofs), None, None))
         pg._touched()
 
 

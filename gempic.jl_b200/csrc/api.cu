@@ -479,6 +479,7 @@ int gempic_hs_get_fields(gempic_handle hs, double *e1, double *e2, double *b, do
     require_init();
     Splitting *h = get<Splitting>(hs, "HamiltonianSplitting");
     Context &c = ctx();
+    if (j2) hs_materialise_j2(*h);
     double *dst[5] = {e1, e2, b, j1, j2};
     for (int k = 0; k < 5; ++k)
         if (dst[k])

@@ -126,14 +126,49 @@ static void fused_pass(Splitting &h, double dt, int n_he, double dt_T)
             launch_pass<Op>(P, &h.scratch, h.acc(), "fused[HE,HE,Hp2,Hp1,Hp2]");
         }
     });
-    allreduce_sum(h.acc(), 3 * h.n);
+    allreduce_sum(h.acc(), 2 * h.n);
     const Maxwell1D &m = *h.maxwell;
-    field_e_from_j(m, h.e2(), h.acc(), 2, 0.5 * dt);             // first Hp2   :173-175
+    // acc = [j2a + j2b | j1].  compute_e_from_j! is linear and nothing reads e2 between the two Hp2 half steps, so
+    // their two solves (:173-175) collapse into one on the summed current
+    field_e_from_j(m, h.e2(), h.acc(), 2, 0.5 * dt);
     field_e_from_j(m, h.e1(), h.acc() + h.n, 1, 1.0);            // Hp1         :111
-    field_e_from_j(m, h.e2(), h.acc() + 2 * h.n, 2, 0.5 * dt);   // second Hp2
-    // j_dofs as the reference leaves them: the last Hp2 zeroed j1 (:132) and holds dt/2 * j2
+    // j_dofs as the reference leaves them: the last Hp2 zeroed j1 (:132) and holds dt/2 * j2b -- a deposit of the
+    // particle state this pass leaves behind, rebuilt by materialise_j2() when somebody looks at it
     GP_CUDA(cudaMemsetAsync(h.j1(), 0, sizeof(double) * h.n, ctx().stream));
-    field_copy(h.j2(), h.acc() + 2 * h.n, h.n);
+    h.j2_stale = true;
+    h.j2_scale = 0.5 * dt;
+}
+
+// j_dofs[2] after a fused pass = dt/2 * sum_p w v2 N(x) over the particles as the pass left them (the second Hp2 of
+// hamiltonian_splitting_1d2v.jl:141-175 deposits after the push and does not change v2).  `kick_dt` != 0 applies the
+// deferred trailing operatorHE kick in the same pass (after the deposit).
+static void materialise_j2_pass(Splitting &h, double kick_dt)
+{
+    const double ws0 = h.pg->charge * h.pg->common_weight * h.ks0->scaling;
+    GP_DISPATCH_DEGREES(h.ks0->degree, h.ks1->degree, {
+        if (kick_dt != 0.0) {
+            using Op = OpHEJ2<D0, D1>;
+            auto P = base_params<Op>(h);
+            P.fields[0] = h.e1T();
+            P.fields[1] = h.e2T();
+            P.op.dtqm = kick_dt * h.pg->q_over_m;
+            P.op.wscale0 = ws0;
+            launch_pass<Op>(P, &h.scratch, h.j2(), "operatorHE+j2");
+        } else {
+            using Op = OpJ2<D0>;
+            auto P = base_params<Op>(h);
+            P.op.wscale0 = ws0;
+            launch_pass<Op>(P, &h.scratch, h.j2(), "j2 deposit");
+        }
+    });
+    allreduce_sum(h.j2(), h.n);
+    field_axpby(h.j2(), 0.0, h.j2(), h.j2_scale, h.n);
+    h.j2_stale = false;
+}
+
+void hs_materialise_j2(Splitting &h)
+{
+    if (h.j2_stale) materialise_j2_pass(h, 0.0);
 }
 
 // The fused pass only pays while its three lane-private grids fit in shared memory (n <~ 35 cells at
@@ -196,7 +231,8 @@ void pg_sync(ParticleGroup &pg)
     Splitting *h = pg.pending;
     if (!h) return;
     pg.pending = nullptr;
-    op_HE_particles(*h, 0.5 * h->pending_dt, h->e1T(), h->e2T());
+    if (h->j2_stale) materialise_j2_pass(*h, 0.5 * h->pending_dt);   // the kick changes v2: rebuild j_dofs[2] first
+    else op_HE_particles(*h, 0.5 * h->pending_dt, h->e1T(), h->e2T());
 }
 
 // ---- {1,1} ----------------------------------------------------------------------------

@@ -130,6 +130,10 @@ struct Splitting : Object {
     PartialScratch scratch;
     int fuse = 0;
     double pending_dt = 0.0;       // dt of the deferred trailing HE kick (ParticleGroup::pending == this)
+    // after a fused pass j2() is not yet the reference's j_dofs[2]: hs_materialise_j2() / pg_sync() rebuild it from the
+    // particles (hs1d.cu).  j2_stale implies ParticleGroup::pending == this.
+    bool j2_stale = false;
+    double j2_scale = 0.0;
     gempic_handle pg_handle = 0;
     // CUDA graph of one Strang step, keyed by dt
     cudaGraphExec_t graph = nullptr;
@@ -200,6 +204,7 @@ inline ParticleGroup *get_pg(gempic_handle h)
 // operator implementations (hs1d.cu / boris.cu)
 void hs_operator(Splitting &h, int op, double dt, bool inside_strang);
 void hs_strang(Splitting &h, double dt, int64_t steps);
+void hs_materialise_j2(Splitting &h);
 void boris_push_v_epart(Boris &s, double dt);
 void boris_push_v_bpart(Boris &s, double dt);
 void boris_push_x_accumulate_j(Boris &s, double dt);

@@ -210,31 +210,37 @@ struct OpHp1 {
 // performs all four: 32 B read + 24 B written per particle instead of 4 passes (168 B).
 // NHE = 2 additionally folds in the trailing HE of the previous step (fields e1T, e2T), which
 // is separated from this step's leading HE only by field-only updates.
-//   source fields: [e1, e2] x NHE, b      grids: j2 (first Hp2), j1, j2 (second Hp2)
+//   source fields: [e1, e2] x NHE, b      grids: j2 (both Hp2 half steps), j1
 //
-// What bounds this pass is the shared-memory pipe (ncu r01c: l1tex data-pipe wavefronts 96 % of
-// peak, a third of them bank conflicts of the field gathers), so it is laid out to minimise
-// wavefronts:
-//   * the kicks of all NHE electric fields are linear in the dofs, so the staged fields are
-//     E1 = sum_h dt_h q/m e1^(h) and E2 likewise: NHE kicks cost one gather each;
-//   * every staged dof exists in 16 lane-interleaved copies (Op::FIELD_COPIES): a gather is
+// What bounds this pass is the shared-memory pipe (ncu r01c/r01d/r01m: l1tex data-pipe wavefronts
+// 87-96 % of peak), so it is laid out to touch as few shared-memory words per particle as possible:
+//   * the fields are staged in pp form (the reference's b_to_pp / evaluate_pp, splinepp.jl:241-285,
+//     pmc1d.jl:242-250): per cell the D+1 polynomial coefficients of  E1 = sum_h dt_h q/m e1^(h),
+//     E2 likewise, and of the PRIMITIVE of b.  One set of D1+1 coefficients of b then serves the
+//     Hp2 gather at the old position, the line integral  int b dx  of Hp1 (Q(t_new) - Q(t_old), plus
+//     whole-cell terms for the few particles that cross a boundary) and the Hp2 gather at the new
+//     position: 3 loads instead of 10, and the kicks of all NHE electric fields cost one Horner each;
+//   * every staged coefficient exists in 16 lane-interleaved copies (Op::FIELD_COPIES): a gather is
 //     conflict free for any cell pattern;
 //   * deposits are read-modify-writes of lane-private grids (pass.cuh), one contiguous window
 //     per grid and particle, issued after the branch-free arithmetic of a whole quad:
-//       j2 (first)   D0+1 slots at the old cell
+//       j2           D0+1 slots at the old cell, then D0+1 slots at the wrapped new position.  Both
+//                    Hp2 half steps add into ONE grid: the two compute_e_from_j!(e2, ., 2) solves are
+//                    linear and nothing reads e2 in between, so e2 -= M0^-1 (dt/2)(j2a + j2b)/dx.
+//                    (j_dofs[2] as the reference leaves it -- dt/2 * j2b -- is rebuilt on demand from
+//                    the particles, hs1d.cu materialise_j2.)
 //       j1           D1+2 slots starting at min(cell_old, cell_new): the old-cell and new-cell
-//                    segments of add_current_update_v! merged, so the same window also gives
-//                    v2 -= q/m sum(window * B)
-//       j2 (second)  D0+1 slots at the wrapped new position
-//   * one block of 8 warps per SM: 8 x 3 lane-private grids + the field copies = 223 KB.
+//                    segments of add_current_update_v! merged;
+//   * one block of 8 warps per SM: 8 x 2 lane-private grids + the coefficient copies = 187 KB.
 // Particles that move more than one cell (or sit outside one period) take the general
-// per-particle code (apply) instead.
+// per-particle code (apply) instead, which reads the dof-form fields from global memory.
 template <int D0, int D1>
 struct FusedWork {
     double x, v1, v2;
     int g0, gw, g0n;
-    bool slow;
-    double d2a[D0 + 1], dj1[D1 + 2], d2b[D0 + 1];
+    bool slow, crossed, moved;   // crossed: x -> x_new left the cell (un-wrapped); moved: the wrapped new cell differs
+    double d2a[D0 + 1], dj1[D1 + 2];
+    double t2b, tn;   // second Hp2 deposit of a particle that changed cell: w v2 and the new offset (rebuilt in commit)
 };
 
 // (c - D) mod n for c - D in [-n, 2n)
@@ -244,59 +250,205 @@ __device__ __forceinline__ int wrap_near(int g, int n)
     return g >= n ? g - n : g;
 }
 
+// coefficient of t^j of piece k of the degree-D uniform B-spline (columns of SplinePP.poly_coeffs,
+// splinepp.jl:39-69, lowest power first)
+template <int D>
+__host__ __device__ constexpr double pp_coef(int k, int j)
+{
+    if (D == 0) return 1.0;
+    if (D == 1) return k == 0 ? (j == 0 ? 1.0 : -1.0) : (j == 0 ? 0.0 : 1.0);
+    if (D == 2) {
+        constexpr double c[3][3] = {{0.5, -1.0, 0.5}, {0.5, 1.0, -1.0}, {0.0, 0.0, 0.5}};
+        return c[k][j];
+    }
+    constexpr double c[4][4] = {{1.0 / 6.0, -0.5, 0.5, -1.0 / 6.0}, {4.0 / 6.0, 0.0, -1.0, 0.5},
+                                {1.0 / 6.0, 0.5, 0.5, -0.5}, {0.0, 0.0, 0.0, 1.0 / 6.0}};
+    return c[k][j];
+}
+
+// p(t) = sum_j c[j*S] t^j
+template <int D, int S>
+__device__ __forceinline__ double horner_s(const double *__restrict__ c, double t)
+{
+    double v = c[D * S];
+#pragma unroll
+    for (int j = D - 1; j >= 0; --j) v = fma(v, t, c[j * S]);
+    return v;
+}
+// h = coefficients of p with Q(t) = t p(t) the primitive of a field: returns Q(t)
+template <int D>
+__device__ __forceinline__ double prim_eval(const double (&h)[D + 1], double t)
+{
+    double p = h[D];
+#pragma unroll
+    for (int j = D - 1; j >= 0; --j) p = fma(p, t, h[j]);
+    return p * t;
+}
+// the field itself, Q'(t) = p(t) + t p'(t)
+template <int D>
+__device__ __forceinline__ double prim_deriv(const double (&h)[D + 1], double t)
+{
+    double p = h[D], dp = 0.0;
+#pragma unroll
+    for (int j = D - 1; j >= 0; --j) {
+        dp = (j == D - 1) ? p : fma(dp, t, p);
+        p = fma(p, t, h[j]);
+    }
+    return D == 0 ? p : fma(dp, t, p);
+}
+// both at the same t
+template <int D>
+__device__ __forceinline__ void prim_both(const double (&h)[D + 1], double t, double &Q, double &f)
+{
+    double p = h[D], dp = 0.0;
+#pragma unroll
+    for (int j = D - 1; j >= 0; --j) {
+        dp = (j == D - 1) ? p : fma(dp, t, p);
+        p = fma(p, t, h[j]);
+    }
+    Q = p * t;
+    f = D == 0 ? p : fma(dp, t, p);
+}
+
+// v = *p if cond (p in shared memory).  A predicated LDS: no branch (the four particle streams of a quad stay
+// interleaved) and no shared-memory wavefront for the lanes that keep their value.
+__device__ __forceinline__ void lds_if(double &v, const double *p, bool cond)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.shared.f64 %0, [%1];\n\t}"
+        : "+d"(v)
+        : "r"((unsigned)__cvta_generic_to_shared(p)), "r"((int)cond));
+}
+// *p += v if cond: predicated read-modify-write of a lane-private slot, ordered after all earlier shared-memory stores
+__device__ __forceinline__ void rmw_if(double *p, double v, bool cond)
+{
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .f64 t;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.shared.f64 t, [%0];\n\t"
+                 "add.f64 t, t, %1;\n\t@q st.shared.f64 [%0], t;\n\t}"
+                 :
+                 : "r"((unsigned)__cvta_generic_to_shared(p)), "d"(v), "r"((int)cond)
+                 : "memory");
+}
+
 template <int D0, int D1, int NHE>
 struct OpStrangFused {
     static constexpr int READ = ROW_X | ROW_V1 | ROW_V2 | ROW_W, WRITE = ROW_X | ROW_V1 | ROW_V2;
     static constexpr int NSRC = 2 * NHE + 1;   // global field vectors in PassParams::fields
-    static constexpr int NF = 3, NG = 3, NS = 0;   // staged: E1, E2, b
+    static constexpr int NC1 = D1 + 1, NC0 = D0 + 1;
+    static constexpr int NF = 2 * NC1 + NC0 + 1;   // staged coefficients per cell: E1 (NC1), E2 (NC0), antiderivative of b (1 + NC1)
+    static constexpr int NG = 2, NS = 0;       // grids: j2 (first + second Hp2), j1
     static constexpr bool DEPOSIT = true;
     static constexpr bool PAIRWISE = true;
     static constexpr int THREADS = 256;
     static constexpr int FIELD_COPIES = 16;
     static constexpr int HALO = (D0 > D1 + 1) ? D0 : D1 + 1;   // widest window minus one
+    static constexpr int FIELD_HALO = 2;                       // pp tables cover the cells -1 .. n
     static constexpr bool CUSTOM_STAGE = true;
     static constexpr int FC = FIELD_COPIES;
+    static constexpr int OFF_E2 = NC1 * FC, OFF_C = (NC1 + NC0) * FC, OFF_B = OFF_C + FC, CELL = NF * FC;   // doubles
     struct Params { double dtqm_e[2], dtqm_p2, dt, qm_dx, wscale0, wscale1_dx; };
     using PP = PassParams<OpStrangFused>;
 
-    // staged fields (each dof in FC copies, periodic halo appended):
-    //   0: sum_h dtqm_e[h] e1^(h)     1: sum_h dtqm_e[h] e2^(h)     2: b
+    // combined electric dofs  sum_h dtqm_e[h] e^(h)[g]  (the kicks are linear in the dofs)
+    static __device__ __forceinline__ double dof_e1(const PP &P, int g)
+    {
+        double c = P.op.dtqm_e[0] * P.fields[0][g];
+        if (NHE == 2) c = fma(P.op.dtqm_e[1], P.fields[2][g], c);
+        return c;
+    }
+    static __device__ __forceinline__ double dof_e2(const PP &P, int g)
+    {
+        double c = P.op.dtqm_e[0] * P.fields[1][g];
+        if (NHE == 2) c = fma(P.op.dtqm_e[1], P.fields[3][g], c);
+        return c;
+    }
+    static __device__ __forceinline__ double dof_b(const PP &P, int g) { return P.fields[2 * NHE][g]; }
+
+    // staged tables, cell i = c + 1 for c = -1 .. n (periodic), coefficient q, copy k:
+    //   sfield[(i * NF + q) * FC + k]
+    //   q in [0, NC1): E1 pp     [NC1, NC1+NC0): E2 pp     then the antiderivative of b,  G_c(t) = C_c + t sum_j h_j t^j
+    //   with h_j = c_j / (j+1) and C_c = int of b from the left end of cell 0 to the left end of cell c: the line
+    //   integral of b along ANY path is G(new) - G(old), whatever the number of cell boundaries crossed.
     static __device__ __forceinline__ void stage(const PP &P, double *sfield, int tid)
     {
-        const int n = P.m.n, nh = n + HALO;
-        for (int i = tid; i < nh; i += THREADS) {
-            const int g = i < n ? i : i - n;
-            double c1 = P.op.dtqm_e[0] * P.fields[0][g], c2 = P.op.dtqm_e[0] * P.fields[1][g];
-            if (NHE == 2) {
-                c1 = fma(P.op.dtqm_e[1], P.fields[2][g], c1);
-                c2 = fma(P.op.dtqm_e[1], P.fields[3][g], c2);
-            }
-            const double bb = P.fields[2 * NHE][g];
+        const int n = P.m.n;
+        for (int i = tid; i < n + FIELD_HALO; i += THREADS) {
+            const int c = i - 1;
+            double co[NF];
 #pragma unroll
-            for (int c = 0; c < FC; ++c) {
-                sfield[(size_t)i * FC + c] = c1;
-                sfield[(size_t)(nh + i) * FC + c] = c2;
-                sfield[(size_t)(2 * nh + i) * FC + c] = bb;
+            for (int q = 0; q < NF; ++q) co[q] = 0.0;
+#pragma unroll
+            for (int k = 0; k <= D1; ++k) {
+                int g = c - D1 + k;
+                g = g < 0 ? g + n : g;
+                g = g >= n ? g - n : g;
+                const double d1 = dof_e1(P, g), db = dof_b(P, g);
+#pragma unroll
+                for (int j = 0; j <= D1; ++j) {
+                    co[j] = fma(d1, pp_coef<D1>(k, j), co[j]);
+                    co[NC1 + NC0 + 1 + j] = fma(db, pp_coef<D1>(k, j) / (double)(j + 1), co[NC1 + NC0 + 1 + j]);
+                }
             }
+#pragma unroll
+            for (int k = 0; k <= D0; ++k) {
+                int g = c - D0 + k;
+                g = g < 0 ? g + n : g;
+                g = g >= n ? g - n : g;
+                const double d2 = dof_e2(P, g);
+#pragma unroll
+                for (int j = 0; j <= D0; ++j) co[NC1 + j] = fma(d2, pp_coef<D0>(k, j), co[NC1 + j]);
+            }
+            {   // C_c: whole-cell integrals of the cells 0 .. c-1 (cell -1: minus that of cell n-1), in a fixed order
+                double cum = 0.0;
+                const int c_hi = c < 0 ? n : c, c_lo = c < 0 ? n - 1 : 0;
+                for (int cc = c_lo; cc < c_hi; ++cc) {
+                    double q1 = 0.0;
+#pragma unroll
+                    for (int k = 0; k <= D1; ++k) {
+                        int g = cc - D1 + k;
+                        g = g < 0 ? g + n : g;
+                        q1 = fma(dof_b(P, g), prim_full<D1>(k), q1);
+                    }
+                    cum += q1;
+                }
+                co[NC1 + NC0] = c < 0 ? -cum : cum;
+            }
+#pragma unroll
+            for (int q = 0; q < NF; ++q)
+#pragma unroll
+                for (int k = 0; k < FC; ++k) sfield[((size_t)i * NF + q) * FC + k] = co[q];
         }
     }
 
-    // general per-particle form (any displacement); sf already points at this lane's field copy
+    // general per-particle form (any displacement): reads the dof-form fields from global memory
     template <bool LP>
-    static __device__ __forceinline__ void apply(Particle &p, const PP &P, const double *sf, const Acc<LP> &acc)
+    static __device__ __forceinline__ void apply(Particle &p, const PP &P, const double *, const Acc<LP> &acc)
     {
-        const int nh = P.m.n + HALO;
-        const double *se1 = sf, *se2 = sf + (size_t)nh * FC, *sb = sf + (size_t)2 * nh * FC;
+        const int n = P.m.n, nh = n + HALO;
         Pos ps = locate(p.x, P.m);
         int g0, g1;
         first_dofs<D0, D1>(ps, P.m, g0, g1);
         double b1[D1 + 1], b0[D0 + 1];
         basis_pp<D1>(ps.t, b1);
         basis_pp<D0>(ps.t, b0);
-        p.v1 += gather_s<D1, FC>(se1 + g1 * FC, b1);
-        p.v2 += gather_s<D0, FC>(se2 + g0 * FC, b0);
+        {
+            double s1 = 0.0, s2 = 0.0, sb = 0.0;
+            int g = g1;
+#pragma unroll
+            for (int k = 0; k <= D1; ++k) {
+                s1 = fma(dof_e1(P, g), b1[k], s1);
+                sb = fma(dof_b(P, g), b1[k], sb);
+                g = wrap_next(g + 1, n);
+            }
+            g = g0;
+#pragma unroll
+            for (int k = 0; k <= D0; ++k) {
+                s2 = fma(dof_e2(P, g), b0[k], s2);
+                g = wrap_next(g + 1, n);
+            }
+            p.v1 += s1;
+            p.v2 += s2;
+            p.v1 = fma(P.op.dtqm_p2 * p.v2, sb, p.v1);
+        }
         const double ws0 = p.w * P.op.wscale0;
-        p.v1 = fma(P.op.dtqm_p2 * p.v2, gather_s<D1, FC>(sb + g1 * FC, b1), p.v1);
         deposit_h<D0, LP>(acc, g0, b0, ws0 * p.v2);
         // Hp1: add_current_update_v! cell by cell
         const double x_new = fma(P.op.dt, p.v1, p.x);
@@ -313,7 +465,7 @@ struct OpStrangFused {
             for (int k = 0; k <= D1; ++k) {
                 const double s = (same ? B[k] : (fwd ? prim_full<D1>(k) : 0.0)) - A[k];
                 acc.add(nh + g + k, ws_dx * s);
-                bsum = fma(s, sb[(g + k) * FC], bsum);
+                bsum = fma(s, dof_b(P, wrap_next(g + k, n)), bsum);
             }
             if (!same) {
                 g = first_dof<D1>(pn, P.m);
@@ -321,7 +473,7 @@ struct OpStrangFused {
                 for (int k = 0; k <= D1; ++k) {
                     const double s = fwd ? B[k] : B[k] - prim_full<D1>(k);
                     acc.add(nh + g + k, ws_dx * s);
-                    bsum = fma(s, sb[(g + k) * FC], bsum);
+                    bsum = fma(s, dof_b(P, wrap_next(g + k, n)), bsum);
                 }
                 const int lo = fwd ? ps.c : pn.c, hi = fwd ? pn.c : ps.c;
                 for (int c = lo + 1; c < hi; ++c) {
@@ -330,7 +482,7 @@ struct OpStrangFused {
                     for (int k = 0; k <= D1; ++k) {
                         const double s = fwd ? prim_full<D1>(k) : -prim_full<D1>(k);
                         acc.add(nh + g + k, ws_dx * s);
-                        bsum = fma(s, sb[(g + k) * FC], bsum);
+                        bsum = fma(s, dof_b(P, wrap_next(g + k, n)), bsum);
                     }
                 }
             }
@@ -342,20 +494,28 @@ struct OpStrangFused {
         first_dofs<D0, D1>(pn, P.m, g0, g1);
         basis_pp<D1>(pn.t, b1);
         basis_pp<D0>(pn.t, b0);
-        p.v1 = fma(P.op.dtqm_p2 * p.v2, gather_s<D1, FC>(sb + g1 * FC, b1), p.v1);
-        deposit_h<D0, LP>(acc, 2 * nh + g0, b0, ws0 * p.v2);
+        {
+            double sb = 0.0;
+            int g = g1;
+#pragma unroll
+            for (int k = 0; k <= D1; ++k) {
+                sb = fma(dof_b(P, g), b1[k], sb);
+                g = wrap_next(g + 1, n);
+            }
+            p.v1 = fma(P.op.dtqm_p2 * p.v2, sb, p.v1);
+        }
+        deposit_h<D0, LP>(acc, g0, b0, ws0 * p.v2);
     }
 
     // out of line and by value, so that the rare call does not pin the particles of the fast
     // path to local memory
     struct XV { double x, v1, v2; };
     template <bool LP>
-    static __device__ __noinline__ XV apply_general(double x, double v1, double v2, double w, const PP &P, const double *sf,
-                                                    double *accp)
+    static __device__ __noinline__ XV apply_general(double x, double v1, double v2, double w, const PP &P, double *accp)
     {
         Particle p{x, v1, v2, w};
         Acc<LP> acc{accp};
-        apply<LP>(p, P, sf, acc);
+        apply<LP>(p, P, nullptr, acc);
         return XV{p.x, p.v1, p.v2};
     }
 
@@ -363,21 +523,25 @@ struct OpStrangFused {
     static __device__ __forceinline__ FusedWork<D0, D1> work(const Particle &p, const PP &P, const double *sf)
     {
         FusedWork<D0, D1> W;
-        const int n = P.m.n, nh = n + HALO;
-        const double *se1 = sf, *se2 = sf + (size_t)nh * FC, *sb = sf + (size_t)2 * nh * FC;
+        const int n = P.m.n;
         double v1 = p.v1, v2 = p.v2;
-        // ---- HE kick(s) and first Hp2 at the old position
+        // ---- HE kick(s) and first Hp2 at the old position: cell polynomials of E1, E2 and of b
         const Pos po = locate(p.x, P.m);
+        const int io = min((unsigned)(po.c + 1), (unsigned)(n + 1));   // table cell (clamped: far-out particles are `slow`)
+        const double *co = sf + (size_t)io * CELL;
         const int g0 = wrap_near(po.c - D0, n);
-        const int g1 = (D1 == D0) ? g0 : wrap_next(g0 + (D0 - D1), n);
-        double A[D1 + 1], b1[D1 + 1], b0[D0 + 1];
+        double A[D1 + 1], b0[D0 + 1];
         prim_pp<D1>(po.t, A);
-        basis_pp<D1>(po.t, b1);
         if constexpr (D1 == D0 - 1) basis_from_prim<D0>(A, b0);
         else basis_pp<D0>(po.t, b0);
-        v1 += gather_s<D1, FC>(se1 + g1 * FC, b1);
-        v2 += gather_s<D0, FC>(se2 + g0 * FC, b0);
-        v1 = fma(P.op.dtqm_p2 * v2, gather_s<D1, FC>(sb + g1 * FC, b1), v1);
+        v1 += horner_s<D1, FC>(co, po.t);
+        v2 += horner_s<D0, FC>(co + OFF_E2, po.t);
+        double ho[D1 + 1];
+#pragma unroll
+        for (int j = 0; j <= D1; ++j) ho[j] = co[OFF_B + j * FC];
+        double Qo, bo;
+        prim_both<D1>(ho, po.t, Qo, bo);
+        v1 = fma(P.op.dtqm_p2 * v2, bo, v1);
         const double ws0 = p.w * P.op.wscale0;
         {
             const double t2 = ws0 * v2;
@@ -396,7 +560,6 @@ struct OpStrangFused {
         const int cmin = min(po.c, pn.c);
         const bool o1 = po.c != cmin, n1 = pn.c != cmin;
         const int gw = wrap_near(cmin - D1, n);
-        double bsum = 0.0;
         const double ws1 = p.w * P.op.wscale1_dx;
 #pragma unroll
         for (int m = 0; m <= D1 + 1; ++m) {
@@ -404,26 +567,51 @@ struct OpStrangFused {
             const double n0 = m <= D1 ? B[m <= D1 ? m : 0] : 0.0, o0 = m <= D1 ? A[m <= D1 ? m : 0] : 0.0;
             const double nn = m == 0 ? F : (m <= D1 ? F + B[m >= 1 ? m - 1 : 0] : B[D1]);
             const double oo = m == 0 ? F : (m <= D1 ? F + A[m >= 1 ? m - 1 : 0] : A[D1]);
-            const double win = (n1 ? nn : n0) - (o1 ? oo : o0);
-            bsum = fma(win, sb[(gw + m) * FC], bsum);
-            W.dj1[m] = ws1 * win;
+            W.dj1[m] = ws1 * ((n1 ? nn : n0) - (o1 ? oo : o0));
         }
-        v2 = fma(-P.op.qm_dx, bsum, v2);
         W.gw = gw;
+        W.crossed = o1 | n1;   // otherwise dj1[D1+1] = 0
+        // v2 -= q/m int b dx along the same path (:416-422) = G(new) - G(old); the cell constants cancel unless a
+        // boundary was crossed, so they (and the new cell's coefficients) are only loaded by the lanes that crossed
+        const int in = min((unsigned)(pn.c + 1), (unsigned)(n + 1));
+        const bool crossed = in != io;
+        const double *cn = sf + (size_t)in * CELL;
+        double hn[D1 + 1], Co = 0.0, Cn = 0.0;
+#pragma unroll
+        for (int j = 0; j <= D1; ++j) {
+            hn[j] = ho[j];
+            lds_if(hn[j], cn + OFF_B + j * FC, crossed);
+        }
+        lds_if(Co, co + OFF_C, crossed);
+        lds_if(Cn, cn + OFF_C, crossed);
+        v2 = fma(-P.op.qm_dx, (prim_eval<D1>(hn, pn.t) - Qo) + (Cn - Co), v2);
         // x = mod(x_new, Lx) for x_new within one period of the domain (:79)
         const double L = P.m.Lx;
         const double x = x_new < 0.0 ? x_new + L : (x_new >= L ? x_new - L : x_new);
         // ---- second Hp2 at the wrapped new position
         const Pos p2 = locate(x, P.m);
         const int g0n = wrap_near(p2.c - D0, n);
-        const int g1n = (D1 == D0) ? g0n : wrap_next(g0n + (D0 - D1), n);
-        basis_pp<D1>(p2.t, b1);
-        basis_pp<D0>(p2.t, b0);
-        v1 = fma(P.op.dtqm_p2 * v2, gather_s<D1, FC>(sb + g1n * FC, b1), v1);
-        {
-            const double t2 = ws0 * v2;
+        const int i2 = min((unsigned)(p2.c + 1), (unsigned)(n + 1));
+        {   // another polynomial only after the trunc quirk at x_new < 0: cell 0 with a negative offset
+            // wraps into cell n-1.  (x_new >= L: cell n of the table is cell 0.)
+            const bool quirk = i2 != in && !(in == n + 1 && i2 == 1);
+            const double *c2 = sf + (size_t)i2 * CELL + OFF_B;
 #pragma unroll
-            for (int k = 0; k <= D0; ++k) W.d2b[k] = t2 * b0[k];
+            for (int j = 0; j <= D1; ++j) lds_if(hn[j], c2 + j * FC, quirk);
+        }
+        v1 = fma(P.op.dtqm_p2 * v2, prim_deriv<D1>(hn, p2.t), v1);
+        basis_pp<D0>(p2.t, b0);
+        {   // both Hp2 deposits go to the same grid: a particle that stays in its cell adds them through ONE window
+            const double t2 = ws0 * v2;
+            W.moved = g0n != g0;
+            double t2s = W.moved ? 0.0 : t2;
+            asm("" : "+d"(t2s));   // keep the select on the scalar (the compiler would otherwise select every product)
+#pragma unroll
+            for (int k = 0; k <= D0; ++k) {
+                W.d2a[k] = fma(t2s, b0[k], W.d2a[k]);
+            }
+            W.t2b = t2;
+            W.tn = p2.t;
         }
         W.g0n = g0n;
         W.x = x;
@@ -436,29 +624,34 @@ struct OpStrangFused {
         return W;
     }
 
-    // the three read-modify-write windows of one particle (lane-private slots: s -> s*32)
+    // the read-modify-write windows of one particle (lane-private slots: s -> s*32): D0+1 slots of j2 at the old cell
+    // (both Hp2 deposits unless the particle changed cell), D1+1 slots of j1, and -- only for the lanes that left their
+    // cell, so without shared-memory wavefronts for the others -- the last j1 slot and the j2 window at the new cell.
     static __device__ __forceinline__ void commit(const FusedWork<D0, D1> &W, double *acc, int nh)
     {
-        double *q0 = acc + (size_t)W.g0 * 32, *q1 = acc + (size_t)(nh + W.gw) * 32, *q2 = acc + (size_t)(2 * nh + W.g0n) * 32;
-        double r0[D0 + 1], r1[D1 + 2], r2[D0 + 1];
+        double *q0 = acc + (size_t)W.g0 * 32, *q1 = acc + (size_t)(nh + W.gw) * 32, *q2 = acc + (size_t)W.g0n * 32;
+        double r0[D0 + 1], r1[D1 + 1];
 #pragma unroll
         for (int k = 0; k <= D0; ++k) r0[k] = q0[k * 32];
 #pragma unroll
-        for (int m = 0; m <= D1 + 1; ++m) r1[m] = q1[m * 32];
-#pragma unroll
-        for (int k = 0; k <= D0; ++k) r2[k] = q2[k * 32];
+        for (int m = 0; m <= D1; ++m) r1[m] = q1[m * 32];
 #pragma unroll
         for (int k = 0; k <= D0; ++k) q0[k * 32] = r0[k] + W.d2a[k];
 #pragma unroll
-        for (int m = 0; m <= D1 + 1; ++m) q1[m * 32] = r1[m] + W.dj1[m];
+        for (int m = 0; m <= D1; ++m) q1[m * 32] = r1[m] + W.dj1[m];
+        rmw_if(q1 + (D1 + 1) * 32, W.dj1[D1 + 1], W.crossed);
+        if (W.moved) {   // keeping these four products live for all lanes spills (254 registers); the few lanes rebuild them
+            double b0[D0 + 1];
+            basis_pp<D0>(W.tn, b0);
 #pragma unroll
-        for (int k = 0; k <= D0; ++k) q2[k * 32] = r2[k] + W.d2b[k];
+            for (int k = 0; k <= D0; ++k) q2[k * 32] += W.t2b * b0[k];
+        }
     }
 
     template <bool LP>
-    static __device__ __forceinline__ void general(Particle &a, const PP &P, const double *sf, const Acc<LP> &acc)
+    static __device__ __forceinline__ void general(Particle &a, const PP &P, const Acc<LP> &acc)
     {
-        const XV r = apply_general<LP>(a.x, a.v1, a.v2, a.w, P, sf, acc.p);
+        const XV r = apply_general<LP>(a.x, a.v1, a.v2, a.w, P, acc.p);
         a.x = r.x; a.v1 = r.v1; a.v2 = r.v2;
     }
 
@@ -468,8 +661,8 @@ struct OpStrangFused {
         const FusedWork<D0, D1> Wa = work(a, P, sf);
         const FusedWork<D0, D1> Wb = work(b, P, sf);
         if (__builtin_expect(Wa.slow | Wb.slow, 0)) {
-            general<LP>(a, P, sf, acc);
-            general<LP>(b, P, sf, acc);
+            general<LP>(a, P, acc);
+            general<LP>(b, P, acc);
             return;
         }
         const int nh = P.m.n + HALO;
@@ -479,31 +672,85 @@ struct OpStrangFused {
         b.x = Wb.x; b.v1 = Wb.v1; b.v2 = Wb.v2;
     }
 
-    // both batches of an iteration: four independent instruction streams before the commits
+    // both batches of an iteration: four independent instruction streams (work_quad), then the deposits (commit_quad)
+    struct Quad { FusedWork<D0, D1> a, b, c, d; };
+    static __device__ __forceinline__ void work_quad(Quad &W, const Particle &a, const Particle &b, const Particle &c,
+                                                     const Particle &d, const PP &P, const double *sf)
+    {
+        W.a = work(a, P, sf);
+        W.b = work(b, P, sf);
+        W.c = work(c, P, sf);
+        W.d = work(d, P, sf);
+    }
+    template <bool LP>
+    static __device__ __forceinline__ void commit_quad(const Quad &W, Particle &a, Particle &b, Particle &c, Particle &d,
+                                                       const PP &P, const Acc<LP> &acc)
+    {
+        if (__builtin_expect(W.a.slow | W.b.slow | W.c.slow | W.d.slow, 0)) {
+            general<LP>(a, P, acc);
+            general<LP>(b, P, acc);
+            general<LP>(c, P, acc);
+            general<LP>(d, P, acc);
+            return;
+        }
+        const int nh = P.m.n + HALO;
+        commit(W.a, acc.p, nh);
+        commit(W.b, acc.p, nh);
+        commit(W.c, acc.p, nh);
+        commit(W.d, acc.p, nh);
+        a.x = W.a.x; a.v1 = W.a.v1; a.v2 = W.a.v2;
+        b.x = W.b.x; b.v1 = W.b.v1; b.v2 = W.b.v2;
+        c.x = W.c.x; c.v1 = W.c.v1; c.v2 = W.c.v2;
+        d.x = W.d.x; d.v1 = W.d.v1; d.v2 = W.d.v2;
+    }
     template <bool LP>
     static __device__ __forceinline__ void apply_quad(Particle &a, Particle &b, Particle &c, Particle &d, const PP &P,
                                                       const double *sf, const Acc<LP> &acc)
     {
-        const FusedWork<D0, D1> Wa = work(a, P, sf);
-        const FusedWork<D0, D1> Wb = work(b, P, sf);
-        const FusedWork<D0, D1> Wc = work(c, P, sf);
-        const FusedWork<D0, D1> Wd = work(d, P, sf);
-        if (__builtin_expect(Wa.slow | Wb.slow | Wc.slow | Wd.slow, 0)) {
-            general<LP>(a, P, sf, acc);
-            general<LP>(b, P, sf, acc);
-            general<LP>(c, P, sf, acc);
-            general<LP>(d, P, sf, acc);
-            return;
-        }
-        const int nh = P.m.n + HALO;
-        commit(Wa, acc.p, nh);
-        commit(Wb, acc.p, nh);
-        commit(Wc, acc.p, nh);
-        commit(Wd, acc.p, nh);
-        a.x = Wa.x; a.v1 = Wa.v1; a.v2 = Wa.v2;
-        b.x = Wb.x; b.v1 = Wb.v1; b.v2 = Wb.v2;
-        c.x = Wc.x; c.v1 = Wc.v1; c.v2 = Wc.v2;
-        d.x = Wd.x; d.v1 = Wd.v1; d.v2 = Wd.v2;
+        Quad W;
+        work_quad(W, a, b, c, d, P, sf);
+        commit_quad<LP>(W, a, b, c, d, P, acc);
+    }
+};
+
+// ---- j2 = sum w v2 N(x) at the current particle state (D0): what the second operatorHp2 of a Strang step
+//      leaves in j_dofs[2] before the dt scaling (hamiltonian_splitting_1d2v.jl:141-175).  The fused pass adds both
+//      half-step currents into one grid; this rebuilds the reference's j_dofs[2] when somebody asks for it.
+template <int D0>
+struct OpJ2 {
+    static constexpr int READ = ROW_X | ROW_V2 | ROW_W, WRITE = 0;
+    static constexpr int NF = 0, NG = 1, NS = 0;
+    static constexpr bool DEPOSIT = true;
+    struct Params { double wscale0; };
+    template <bool LP>
+    static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpJ2> &P, const double *, const Acc<LP> &acc)
+    {
+        const Pos ps = locate(p.x, P.m);
+        double b0[D0 + 1];
+        basis_pp<D0>(ps.t, b0);
+        deposit_h<D0, LP>(acc, first_dof<D0>(ps, P.m), b0, (p.w * P.op.wscale0) * p.v2);
+    }
+};
+
+// ---- the same deposit fused with the deferred operatorHE kick that follows it (pg_sync, hs1d.cu).  fields: [e1, e2]
+template <int D0, int D1>
+struct OpHEJ2 {
+    static constexpr int READ = ROW_X | ROW_V1 | ROW_V2 | ROW_W, WRITE = ROW_V1 | ROW_V2;
+    static constexpr int NF = 2, NG = 1, NS = 0;
+    static constexpr bool DEPOSIT = true;
+    struct Params { double dtqm, wscale0; };
+    template <bool LP>
+    static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpHEJ2> &P, const double *sf, const Acc<LP> &acc)
+    {
+        const int nh = P.m.n + kHalo;
+        const Pos ps = locate(p.x, P.m);
+        int g0, g1;
+        first_dofs<D0, D1>(ps, P.m, g0, g1);
+        double b1[D1 + 1], b0[D0 + 1];
+        basis_pp<D1>(ps.t, b1);
+        basis_pp<D0>(ps.t, b0);
+        deposit_h<D0, LP>(acc, g0, b0, (p.w * P.op.wscale0) * p.v2);
+        kick_e<D0, D1>(p, g0, g1, b0, b1, sf, sf + nh, P.op.dtqm);
     }
 };
 

@@ -188,6 +188,8 @@ int gempic_hs_create(int D, int V, gempic_handle maxwell, gempic_handle pmc0, ge
 int gempic_hs_destroy(gempic_handle hs);
 /* e_dofs/b_dofs are aliased caller arrays in the reference (:80-81): copy them in / out. */
 int gempic_hs_set_fields(gempic_handle hs, const double *e1, const double *e2, const double *b);
+/* NULL pointers are skipped.  j1/j2 = j_dofs (:51), scratch of the splitting object: after a fused strang_splitting
+ * a non-NULL j2 costs one extra deposit pass that rebuilds the reference's j_dofs[2] from the particles. */
 int gempic_hs_get_fields(gempic_handle hs, double *e1, double *e2, double *b, double *j1, double *j2);
 /* device-resident calls: asynchronous on gempic_stream() */
 int gempic_hs_operator(gempic_handle hs, int op, double dt);          /* operatorHp1/Hp2/HE/HB */

@@ -193,6 +193,8 @@ end
 # ---- HamiltonianSplitting{D,V} (src/hamiltonian_splitting.jl:20-86) -----------------------------
 # e_dofs / b_dofs stay the caller's arrays (aliased, :80-81): every call copies them in and the
 # updated values back (3 x n doubles), which is what the reference's tests read after each operator.
+# j_dofs (:51) is scratch owned by the splitting object; no caller of the reference reads it.  It stays on the device and
+# `h.j_dofs` reads it back on access (getproperty below), so a strang_splitting! call moves 3 x n doubles each way.
 struct HamiltonianSplitting{D,V}
     dims::Tuple{Int64,Int64}
     maxwell_solver::Maxwell1DFEM
@@ -201,7 +203,7 @@ struct HamiltonianSplitting{D,V}
     particle_group::ParticleGroup
     e_dofs::Array{Array{Float64,1}}
     b_dofs::Array{Float64,1}
-    j_dofs::Array{Array{Float64,1}}
+    j_host::Array{Array{Float64,1}}
     handle::Handle
     function HamiltonianSplitting{D,V}(maxwell_solver, kernel_smoother_0, kernel_smoother_1, particle_group,
                                        e_dofs, b_dofs; fuse = true) where {D,V}
@@ -213,11 +215,18 @@ struct HamiltonianSplitting{D,V}
         return new((D, V), maxwell_solver, kernel_smoother_0, kernel_smoother_1, particle_group, e_dofs, b_dofs, j_dofs, h[])
     end
 end
+function Base.getproperty(h::HamiltonianSplitting, name::Symbol)
+    name === :j_dofs || return getfield(h, name)
+    j = getfield(h, :j_host)   # after a fused strang_splitting! this rebuilds j_dofs[2] from the particles (DESIGN.md section 6)
+    check(ccall((:gempic_hs_get_fields, LIB), Cint, (Handle, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                getfield(h, :handle), C_NULL, C_NULL, C_NULL, j[1], j[2]))
+    return j
+end
 const OP_HP1, OP_HP2, OP_HE, OP_HB = Cint(1), Cint(2), Cint(3), Cint(4)
 _op(h::HamiltonianSplitting, op::Cint, dt::Float64) =
     check(ccall((:gempic_hs_operator_host, LIB), Cint,
                 (Handle, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
-                h.handle, op, dt, h.e_dofs[1], h.e_dofs[2], h.b_dofs, h.j_dofs[1], h.j_dofs[2]))
+                h.handle, op, dt, h.e_dofs[1], h.e_dofs[2], h.b_dofs, C_NULL, C_NULL))
 operatorHp1(h::HamiltonianSplitting, dt::Float64) = _op(h, OP_HP1, dt)   # src/hamiltonian_splitting_1d2v.jl:41-112 / _1d1v.jl:63-98
 operatorHp2(h::HamiltonianSplitting, dt::Float64) = _op(h, OP_HP2, dt)   # :129-176
 operatorHE(h::HamiltonianSplitting, dt::Float64) = _op(h, OP_HE, dt)     # :191-219
@@ -225,7 +234,7 @@ operatorHB(h::HamiltonianSplitting, dt::Float64) = _op(h, OP_HB, dt)     # :234-
 strang_splitting!(h::HamiltonianSplitting, dt::Float64, number_steps::Int) =   # src/hamiltonian_splitting.jl:98-108
     check(ccall((:gempic_hs_strang_splitting_host, LIB), Cint,
                 (Handle, Cdouble, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
-                h.handle, dt, number_steps, h.e_dofs[1], h.e_dofs[2], h.b_dofs, h.j_dofs[1], h.j_dofs[2]))
+                h.handle, dt, number_steps, h.e_dofs[1], h.e_dofs[2], h.b_dofs, C_NULL, C_NULL))
 
 # ---- HamiltonianSplittingBoris (src/hamiltonian_splitting_boris.jl:23-88) -----------------------
 struct HamiltonianSplittingBoris

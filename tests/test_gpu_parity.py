@@ -150,6 +150,27 @@ def test_deferred_trailing_kick_is_invisible(orc, gp):
     assert rel_err(e1c, e1b) < 1e-10 and rel_err(sg.e1, so.e1) < 1e-10 and rel_err(sg.b, so.b) < 1e-10
 
 
+def test_fused_j_dofs_rebuilt_on_demand(orc, gp):
+    """the fused pass adds both Hp2 half-step currents into one grid (their two e2 solves are linear); `j_dofs` as the
+    reference leaves it -- zero j1, dt/2 * j2 of the SECOND Hp2 -- is rebuilt from the particles when it is looked at:
+    by a stand-alone deposit while the trailing HE kick is still pending, or inside the pass that applies that kick"""
+    n = 40_000
+    state = landau_state(n, L_LANDAU, seed=3)
+    so, sg = both(orc, gp, state, L_LANDAU, nx=32)
+    so.init_fields(b_amp=5e-2, e2_amp=1e-2), sg.init_fields(b_amp=5e-2, e2_amp=1e-2)
+    ho, hg = so.splitting(), sg.splitting(resident=True)
+    hg.set_fusion(True)
+    ho.strang_splitting(0.05, 2), hg.strang_splitting(0.05, 2)
+    jg = [j.copy() for j in hg.j_dofs]                      # kick pending: stand-alone j2 deposit
+    assert np.max(np.abs(jg[0])) == 0.0 and rel_err(jg[1], ho.j_dofs[1]) < 1e-11
+    assert np.array_equal(hg.j_dofs[1], jg[1])              # idempotent
+    ho.strang_splitting(0.05, 1), hg.strang_splitting(0.05, 1)
+    assert particle_err(sg.particles(), so.particles(), L_LANDAU) < 1e-11   # download: kick + j2 deposit in one pass
+    assert rel_err(hg.j_dofs[1], ho.j_dofs[1]) < 1e-11
+    hg.sync_fields()
+    check_fields(so, sg, tol=1e-11)
+
+
 def test_multicell_and_backward_crossings(orc, gp):
     # fast particles: several cells per step in both directions, x_new < 0 (trunc quirk, SURVEY Q1)
     n = 20_000
