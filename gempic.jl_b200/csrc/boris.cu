@@ -79,18 +79,32 @@ static void boris_step(Boris &s, double dt)   // :132-177
     field_b_from_e(m, s.f(GEMPIC_F_B), dt, s.f(GEMPIC_F_E2_MID));
     field_axpby(s.f(GEMPIC_F_B_MID), 1.0, s.f(GEMPIC_F_B), 1.0, s.n);   // b_mid + b
     field_axpby(s.f(GEMPIC_F_B_MID), 0.0, s.f(GEMPIC_F_B), 0.5, s.n);   // (..) * 0.5
-    // (2)+(3) fused particle pass
+    // (2)+(3) fused particle pass while its lane-private grids and pp tables fit in shared memory (n <~ 40 cells at
+    // degree 3), else the four reference loops one by one
+    bool fused = false;
     GP_DISPATCH_DEGREES(s.ks0->degree, s.ks1->degree, {
         using Op = OpBorisStep<D0, D1>;
         auto P = base_params<Op>(s);
-        P.fields[0] = s.f(GEMPIC_F_E1_MID);
-        P.fields[1] = s.f(GEMPIC_F_E2_MID);
-        P.fields[2] = s.f(GEMPIC_F_B_MID);
-        const double cq = s.pg->charge * s.pg->common_weight;
-        P.op = {dt, (0.5 * dt) * s.pg->q_over_m, s.pg->q_over_m * 0.5 * dt, cq * s.ks0->scaling, cq * s.ks1->scaling};
-        launch_pass<Op>(P, &s.scratch, s.f(GEMPIC_F_J1), "boris_step");
+        const size_t need = ((size_t)Op::NF * (P.m.n + Op::FIELD_HALO) * Op::FC + (size_t)acc_slots<Op>(P.m.n) * 32 * (Op::THREADS / 32)) *
+                            sizeof(double);
+        if (need <= kSmemMaxOptin) {
+            fused = true;
+            P.fields[0] = s.f(GEMPIC_F_E1_MID);
+            P.fields[1] = s.f(GEMPIC_F_E2_MID);
+            P.fields[2] = s.f(GEMPIC_F_B_MID);
+            const double cq = s.pg->charge * s.pg->common_weight;
+            P.op = {dt, (0.5 * dt) * s.pg->q_over_m, s.pg->q_over_m * 0.5 * dt, cq * s.ks0->scaling, cq * s.ks1->scaling};
+            launch_pass<Op>(P, &s.scratch, s.f(GEMPIC_F_J1), "boris_step");
+        }
     });
-    allreduce_sum(s.f(GEMPIC_F_J1), 2 * s.n);
+    if (fused) {
+        allreduce_sum(s.f(GEMPIC_F_J1), 2 * s.n);
+    } else {
+        boris_push_v_epart(s, 0.5 * dt);
+        boris_push_v_bpart(s, dt);
+        boris_push_v_epart(s, 0.5 * dt);
+        boris_push_x_accumulate_j(s, dt);
+    }
     // (4)
     field_copy(s.f(GEMPIC_F_E1), s.f(GEMPIC_F_E1_MID), 2 * s.n);
     boris_fields_after_push(s, dt, dt);

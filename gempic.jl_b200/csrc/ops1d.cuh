@@ -275,6 +275,23 @@ __device__ __forceinline__ double horner_s(const double *__restrict__ c, double 
     for (int j = D - 1; j >= 0; --j) v = fma(v, t, c[j * S]);
     return v;
 }
+// polynomial of a degree-D spline field in cell c (b_to_pp, splinepp.jl:241-261): co[j] = sum_k dof((c-D+k) mod n) pp_coef(k, j)
+template <int D, class F>
+__device__ __forceinline__ void cell_poly(int c, int n, F dof, double *co)
+{
+#pragma unroll
+    for (int j = 0; j <= D; ++j) co[j] = 0.0;
+#pragma unroll
+    for (int k = 0; k <= D; ++k) {
+        int g = c - D + k;
+        g = g < 0 ? g + n : g;
+        g = g >= n ? g - n : g;
+        const double d = dof(g);
+#pragma unroll
+        for (int j = 0; j <= D; ++j) co[j] = fma(d, pp_coef<D>(k, j), co[j]);
+    }
+}
+
 // h = coefficients of p with Q(t) = t p(t) the primitive of a field: returns Q(t)
 template <int D>
 __device__ __forceinline__ double prim_eval(const double (&h)[D + 1], double t)
@@ -373,29 +390,11 @@ struct OpStrangFused {
         for (int i = tid; i < n + FIELD_HALO; i += THREADS) {
             const int c = i - 1;
             double co[NF];
+            cell_poly<D1>(c, n, [&](int g) { return dof_e1(P, g); }, co);
+            cell_poly<D0>(c, n, [&](int g) { return dof_e2(P, g); }, co + NC1);
+            cell_poly<D1>(c, n, [&](int g) { return dof_b(P, g); }, co + NC1 + NC0 + 1);
 #pragma unroll
-            for (int q = 0; q < NF; ++q) co[q] = 0.0;
-#pragma unroll
-            for (int k = 0; k <= D1; ++k) {
-                int g = c - D1 + k;
-                g = g < 0 ? g + n : g;
-                g = g >= n ? g - n : g;
-                const double d1 = dof_e1(P, g), db = dof_b(P, g);
-#pragma unroll
-                for (int j = 0; j <= D1; ++j) {
-                    co[j] = fma(d1, pp_coef<D1>(k, j), co[j]);
-                    co[NC1 + NC0 + 1 + j] = fma(db, pp_coef<D1>(k, j) / (double)(j + 1), co[NC1 + NC0 + 1 + j]);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k <= D0; ++k) {
-                int g = c - D0 + k;
-                g = g < 0 ? g + n : g;
-                g = g >= n ? g - n : g;
-                const double d2 = dof_e2(P, g);
-#pragma unroll
-                for (int j = 0; j <= D0; ++j) co[NC1 + j] = fma(d2, pp_coef<D0>(k, j), co[NC1 + j]);
-            }
+            for (int j = 1; j <= D1; ++j) co[NC1 + NC0 + 1 + j] *= 1.0 / (double)(j + 1);
             {   // C_c: whole-cell integrals of the cells 0 .. c-1 (cell -1: minus that of cell n-1), in a fixed order
                 double cum = 0.0;
                 const int c_hi = c < 0 ? n : c, c_lo = c < 0 ? n - 1 : 0;
@@ -853,36 +852,188 @@ struct OpBorisX {
 //      (hamiltonian_splitting_boris.jl:146-155; no field changes in between, so the four
 //      reference loops collapse into one pass: 56 B/particle instead of 160).
 //      fields: [e1_mid, e2_mid, b_mid]
+// Laid out like the fused Strang pass (shared-memory pipe and latency bound): the three fields are staged in pp form
+// (evaluate_pp, pmc1d.jl:242-250) with the kick factors folded in -- all three are gathered at the same point, so the
+// B-spline bases are only needed for the deposits at the midpoint; 16 lane-interleaved copies; four particles per lane
+// run their branch-free arithmetic before the lane-private read-modify-writes; one block of 8 warps per SM.
+template <int D0, int D1>
+struct BorisWork {
+    double x, v1, v2;
+    int g0, g1;
+    bool slow;
+    double d1[D1 + 1], d0[D0 + 1];
+};
 template <int D0, int D1>
 struct OpBorisStep {
     static constexpr int READ = ROW_X | ROW_V1 | ROW_V2 | ROW_W, WRITE = ROW_X | ROW_V1 | ROW_V2;
-    static constexpr int NF = 3, NG = 2, NS = 0;
+    static constexpr int NC1 = D1 + 1, NC0 = D0 + 1;
+    static constexpr int NF = 2 * NC1 + NC0, NG = 2, NS = 0;   // staged per cell: half_dtqm e1 (NC1), half_dtqm e2 (NC0), qmdt b (NC1)
     static constexpr bool DEPOSIT = true;
-    // like the fused Strang pass this one is bound by the shared-memory pipe: conflict-free gathers from 16
-    // lane-interleaved field copies, one block of 8 warps per SM
+    static constexpr bool PAIRWISE = true;
     static constexpr int THREADS = 256;
     static constexpr int FIELD_COPIES = 16;
+    static constexpr int FIELD_HALO = 2;   // pp tables cover the cells -1 .. n
+    static constexpr bool CUSTOM_STAGE = true;
     static constexpr int FC = FIELD_COPIES;
+    static constexpr int OFF_E2 = NC1 * FC, OFF_B = (NC1 + NC0) * FC, CELL = NF * FC;
     struct Params { double dt, half_dtqm, qmdt, wscale0, wscale1; };
-    template <bool LP>
-    static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpBorisStep> &P, const double *sf, const Acc<LP> &acc)
+    using PP = PassParams<OpBorisStep>;
+
+    static __device__ __forceinline__ void stage(const PP &P, double *sfield, int tid)
     {
-        const int nh = P.m.n + kHalo;
+        const int n = P.m.n;
+        for (int i = tid; i < n + FIELD_HALO; i += THREADS) {
+            double co[NF];
+            cell_poly<D1>(i - 1, n, [&](int g) { return P.op.half_dtqm * P.fields[0][g]; }, co);
+            cell_poly<D0>(i - 1, n, [&](int g) { return P.op.half_dtqm * P.fields[1][g]; }, co + NC1);
+            cell_poly<D1>(i - 1, n, [&](int g) { return P.op.qmdt * P.fields[2][g]; }, co + NC1 + NC0);
+#pragma unroll
+            for (int q = 0; q < NF; ++q)
+#pragma unroll
+                for (int k = 0; k < FC; ++k) sfield[((size_t)i * NF + q) * FC + k] = co[q];
+        }
+    }
+
+    // general per-particle form (any position / displacement): dof-form fields from global memory
+    template <bool LP>
+    static __device__ __forceinline__ void apply(Particle &p, const PP &P, const double *, const Acc<LP> &acc)
+    {
+        const int n = P.m.n;
         const Pos ps = locate(p.x, P.m);
         int g0, g1;
         first_dofs<D0, D1>(ps, P.m, g0, g1);
         double b1[D1 + 1], b0[D0 + 1];
         basis_pp<D1>(ps.t, b1);
         basis_pp<D0>(ps.t, b0);
-        const double e1 = gather_s<D1, FC>(sf + (size_t)g1 * FC, b1);
-        const double e2 = gather_s<D0, FC>(sf + (size_t)(nh + g0) * FC, b0);
-        const double bf = gather_s<D1, FC>(sf + (size_t)(2 * nh + g1) * FC, b1);
+        double e1 = 0.0, e2 = 0.0, bf = 0.0;
+        int g = g1;
+#pragma unroll
+        for (int k = 0; k <= D1; ++k) {
+            e1 = fma(P.fields[0][g], b1[k], e1);
+            bf = fma(P.fields[2][g], b1[k], bf);
+            g = wrap_next(g + 1, n);
+        }
+        g = g0;
+#pragma unroll
+        for (int k = 0; k <= D0; ++k) {
+            e2 = fma(P.fields[1][g], b0[k], e2);
+            g = wrap_next(g + 1, n);
+        }
         p.v1 = fma(P.op.half_dtqm, e1, p.v1);
         p.v2 = fma(P.op.half_dtqm, e2, p.v2);
         boris_rotate(p, bf, P.op.qmdt);
         p.v1 = fma(P.op.half_dtqm, e1, p.v1);
         p.v2 = fma(P.op.half_dtqm, e2, p.v2);
         boris_push_x<D0, D1, LP>(p, P.op.dt, P.op.wscale0, P.op.wscale1, acc, P.m);
+    }
+    struct XV { double x, v1, v2; };
+    template <bool LP>
+    static __device__ __noinline__ XV apply_general(double x, double v1, double v2, double w, const PP &P, double *accp)
+    {
+        Particle p{x, v1, v2, w};
+        Acc<LP> acc{accp};
+        apply<LP>(p, P, nullptr, acc);
+        return XV{p.x, p.v1, p.v2};
+    }
+    template <bool LP>
+    static __device__ __forceinline__ void general(Particle &a, const PP &P, const Acc<LP> &acc)
+    {
+        const XV r = apply_general<LP>(a.x, a.v1, a.v2, a.w, P, acc.p);
+        a.x = r.x; a.v1 = r.v1; a.v2 = r.v2;
+    }
+
+    // branch-free arithmetic of one particle; no shared-memory writes
+    static __device__ __forceinline__ BorisWork<D0, D1> work(const Particle &p, const PP &P, const double *sf)
+    {
+        BorisWork<D0, D1> W;
+        const int n = P.m.n;
+        const Pos po = locate(p.x, P.m);
+        const double *co = sf + (size_t)min((unsigned)(po.c + 1), (unsigned)(n + 1)) * CELL;
+        const double e1 = horner_s<D1, FC>(co, po.t);            // half_dtqm * E1(x)
+        const double e2 = horner_s<D0, FC>(co + OFF_E2, po.t);   // half_dtqm * E2(x)
+        const double beta = horner_s<D1, FC>(co + OFF_B, po.t);  // q/m dt/2 * B(x)
+        double v1 = p.v1 + e1, v2 = p.v2 + e2;
+        {   // push_v_bpart! :211-233
+            double M11 = 1.0 / fma(beta, beta, 1.0);
+            const double M12 = (M11 * beta) * 2.0;
+            M11 = M11 * fma(-beta, beta, 1.0);
+            const double r1 = fma(M12, v2, M11 * v1);
+            const double r2 = fma(M11, v2, -(M12 * v1));
+            v1 = r1 + e1;
+            v2 = r2 + e2;
+        }
+        // push_x_accumulate_j! :250-288: deposits at the un-wrapped midpoint
+        const double x_new = fma(P.op.dt, v1, p.x);
+        const Pos pm = locate((p.x + x_new) * 0.5, P.m);
+        const int g0 = wrap_near(pm.c - D0, n);
+        const int g1 = (D1 == D0) ? g0 : wrap_next(g0 + (D0 - D1), n);
+        double b1[D1 + 1], b0[D0 + 1];
+        basis_pp<D1>(pm.t, b1);
+        basis_pp<D0>(pm.t, b0);
+        const double w1 = (p.w * P.op.wscale1) * v1, w0 = (p.w * P.op.wscale0) * v2;
+#pragma unroll
+        for (int k = 0; k <= D1; ++k) W.d1[k] = w1 * b1[k];
+#pragma unroll
+        for (int k = 0; k <= D0; ++k) W.d0[k] = w0 * b0[k];
+        W.g0 = g0;
+        W.g1 = g1;
+        const double L = P.m.Lx;
+        W.x = x_new < 0.0 ? x_new + L : (x_new >= L ? x_new - L : x_new);
+        W.v1 = v1;
+        W.v2 = v2;
+        const unsigned span = (unsigned)(n + 2);
+        W.slow = (unsigned)(po.c + 1) >= span || (unsigned)(pm.c + 1) >= span || !(x_new >= -L && x_new < 2.0 * L) || n < 8;
+        return W;
+    }
+    static __device__ __forceinline__ void commit(const BorisWork<D0, D1> &W, double *acc, int nh)
+    {
+        double *q1 = acc + (size_t)W.g1 * 32, *q0 = acc + (size_t)(nh + W.g0) * 32;
+        double r1[D1 + 1], r0[D0 + 1];
+#pragma unroll
+        for (int k = 0; k <= D1; ++k) r1[k] = q1[k * 32];
+#pragma unroll
+        for (int k = 0; k <= D0; ++k) r0[k] = q0[k * 32];
+#pragma unroll
+        for (int k = 0; k <= D1; ++k) q1[k * 32] = r1[k] + W.d1[k];
+#pragma unroll
+        for (int k = 0; k <= D0; ++k) q0[k * 32] = r0[k] + W.d0[k];
+    }
+    template <bool LP>
+    static __device__ __forceinline__ void apply_pair(Particle &a, Particle &b, const PP &P, const double *sf, const Acc<LP> &acc)
+    {
+        const BorisWork<D0, D1> Wa = work(a, P, sf), Wb = work(b, P, sf);
+        if (__builtin_expect(Wa.slow | Wb.slow, 0)) {
+            general<LP>(a, P, acc);
+            general<LP>(b, P, acc);
+            return;
+        }
+        const int nh = P.m.n + kHalo;
+        commit(Wa, acc.p, nh);
+        commit(Wb, acc.p, nh);
+        a.x = Wa.x; a.v1 = Wa.v1; a.v2 = Wa.v2;
+        b.x = Wb.x; b.v1 = Wb.v1; b.v2 = Wb.v2;
+    }
+    template <bool LP>
+    static __device__ __forceinline__ void apply_quad(Particle &a, Particle &b, Particle &c, Particle &d, const PP &P,
+                                                      const double *sf, const Acc<LP> &acc)
+    {
+        const BorisWork<D0, D1> Wa = work(a, P, sf), Wb = work(b, P, sf), Wc = work(c, P, sf), Wd = work(d, P, sf);
+        if (__builtin_expect(Wa.slow | Wb.slow | Wc.slow | Wd.slow, 0)) {
+            general<LP>(a, P, acc);
+            general<LP>(b, P, acc);
+            general<LP>(c, P, acc);
+            general<LP>(d, P, acc);
+            return;
+        }
+        const int nh = P.m.n + kHalo;
+        commit(Wa, acc.p, nh);
+        commit(Wb, acc.p, nh);
+        commit(Wc, acc.p, nh);
+        commit(Wd, acc.p, nh);
+        a.x = Wa.x; a.v1 = Wa.v1; a.v2 = Wa.v2;
+        b.x = Wb.x; b.v1 = Wb.v1; b.v2 = Wb.v2;
+        c.x = Wc.x; c.v1 = Wc.v1; c.v2 = Wc.v2;
+        d.x = Wd.x; d.v1 = Wd.v1; d.v2 = Wd.v2;
     }
 };
 

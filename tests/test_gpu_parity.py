@@ -255,6 +255,24 @@ def test_boris(orc, gp):
         assert rel_err(bg.j_dofs[k], bo.j_dofs[k]) < 1e-11
 
 
+@pytest.mark.parametrize("nx,deg0,deg1,sigma1", [(32, 3, 2, 6.0), (128, 3, 2, 1.0), (24, 2, 1, 1.0), (16, 1, 0, 2.0), (32, 3, 3, 1.0)])
+def test_boris_fused_step_cases(orc, gp, nx, deg0, deg1, sigma1):
+    """the one-pass Boris step on other degrees, with multi-cell displacements (general path) and on a grid whose
+    lane-private copies do not fit in shared memory (four separate passes)"""
+    n = 30_001
+    state = landau_state(n, L_LANDAU, seed=nx + deg0, sigma=(sigma1, 1.0))
+    so, sg = both(orc, gp, state, L_LANDAU, nx=nx, deg0=deg0, deg1=deg1)
+    so.init_fields(b_amp=5e-2, e2_amp=1e-2), sg.init_fields(b_amp=5e-2, e2_amp=1e-2)
+    bo, bg = so.boris(), sg.boris()
+    bo.staggering(0.05), bg.staggering(0.05)
+    bo.strang_splitting(0.05, 3), bg.strang_splitting(0.05, 3)
+    assert particle_err(sg.particles(), so.particles(), L_LANDAU) < 1e-11
+    for name in ("e1", "e2", "b"):
+        assert rel_err(getattr(sg, name), getattr(so, name)) < 1e-11, name
+    for k in range(2):
+        assert rel_err(bg.j_dofs[k], bo.j_dofs[k]) < 1e-11
+
+
 def test_diagnostics_write_step(orc, gp):
     n = 50_000
     state = weibel_state(n, L_WEIBEL, seed=2)

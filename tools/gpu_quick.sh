@@ -16,7 +16,7 @@ try:
 except Exception as e:
     print("bench parse failed", e); print(open("$OUT/${TAG}_bench.err").read()[-3000:])
 PY
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:OpStrangFused -s 4 -c 1 -f \
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:${KREGEX:-OpStrangFused} -s ${KSKIP:-4} -c 1 -f \
     -o $OUT/${TAG}_prof python bench.py --steps 2 --warmup 3 --no-cpu "$@" > $OUT/${TAG}_ncu.log 2>&1; echo "ncu rc=$?"
 ncu -i $OUT/${TAG}_prof.ncu-rep --page raw --csv > $OUT/${TAG}_prof_raw.csv 2>/dev/null
 ncu -i $OUT/${TAG}_prof.ncu-rep --page source --csv > $OUT/${TAG}_prof_source.csv 2>/dev/null
