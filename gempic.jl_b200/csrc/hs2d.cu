@@ -130,6 +130,23 @@ template <int D0>
 struct Tile {
     static constexpr int W = 2 * kR2 + 1 + D0;
     static constexpr int SLOTS = W * W;
+    // Row stride of the warp-shared FIELD tiles.  After some drift the lanes of a half-warp sit in cells that differ by
+    // up to two in either direction, so two lanes read words (dy * WS + dx) doubles apart; with WS = W = 8 the common
+    // pair dy = +-2, dx = 0 falls into the same bank (16 doubles = 32 banks): a 2-way conflict on almost every gather
+    // (ncu r01h: 35 % of the shared wavefronts of Op2HE).  WS is the smallest stride >= W for which no offset with
+    // |dx|, |dy| <= 2 is a multiple of 16 doubles.
+    static constexpr int field_stride()
+    {
+        for (int S = W;; ++S) {
+            bool ok = true;
+            for (int dy = 1; dy <= 2; ++dy)
+                for (int dx = -2; dx <= 2; ++dx)
+                    if ((dy * S + dx) % 16 == 0) ok = false;
+            if (ok) return S;
+        }
+    }
+    static constexpr int WS = field_stride();
+    static constexpr int FS = WS * W;   // doubles of one field tile
 };
 
 // sum_{b<=DY} (sum_{a<=DX} q[b*W + a] bx[a]) by[b] on a shared field tile (q = first dof of the stencil)
@@ -176,7 +193,7 @@ struct Op2HE {
 
     static __device__ __forceinline__ void apply(Part2 &p, const PP &P, const double *ft, double *, int bx, int by)
     {
-        constexpr int D1 = D0 - 1, W = Tile<D0>::W, WW = W * W;
+        constexpr int D1 = D0 - 1, WS = Tile<D0>::WS, FS = Tile<D0>::FS;
         int cx, cy;
         double tx, ty;
         locate2<0>(p.x[0], P.m, cx, tx);
@@ -187,10 +204,10 @@ struct Op2HE {
             double bx0[D0 + 1], bx1[D1 + 1], by0[D0 + 1], by1[D1 + 1];
             basis_pp<D0>(tx, bx0); basis_pp<D1>(tx, bx1);
             basis_pp<D0>(ty, by0); basis_pp<D1>(ty, by1);
-            const double *q = ft + (ry + kR2) * W + rx + kR2;
-            e.v0 = eval_tile<D1, D0, W>(q + 1, bx1, by0);
-            e.v1 = eval_tile<D0, D1, W>(q + WW + W, bx0, by1);
-            e.v2 = eval_tile<D0, D0, W>(q + 2 * WW, bx0, by0);
+            const double *q = ft + (ry + kR2) * WS + rx + kR2;
+            e.v0 = eval_tile<D1, D0, WS>(q + 1, bx1, by0);
+            e.v1 = eval_tile<D0, D1, WS>(q + FS + WS, bx0, by1);
+            e.v2 = eval_tile<D0, D0, WS>(q + 2 * FS, bx0, by0);
         } else {
             e = slow(p.x[0], p.x[1], P);
         }
@@ -282,7 +299,7 @@ struct Op2Hp3 {
 
     static __device__ __forceinline__ void apply(Part2 &p, const PP &P, const double *ft, double *tile, int bx, int by)
     {
-        constexpr int D1 = D0 - 1, W = Tile<D0>::W, WW = W * W;
+        constexpr int D1 = D0 - 1, W = Tile<D0>::W, WS = Tile<D0>::WS, FS = Tile<D0>::FS;
         int cx, cy;
         double tx, ty;
         locate2<0>(p.x[0], P.m, cx, tx);
@@ -296,9 +313,9 @@ struct Op2Hp3 {
             basis_pp<D0>(tx, bx0); basis_pp<D1>(tx, bx1);
             basis_pp<D0>(ty, by0); basis_pp<D1>(ty, by1);
             const int lx = rx + kR2, ly = ry + kR2;
-            const double *q = ft + ly * W + lx;
-            B1 = eval_tile<D0, D1, W>(q + W, bx0, by1);
-            B2 = eval_tile<D1, D0, W>(q + WW + 1, bx1, by0);
+            const double *q = ft + ly * WS + lx;
+            B1 = eval_tile<D0, D1, WS>(q + WS, bx0, by1);
+            B2 = eval_tile<D1, D0, WS>(q + FS + 1, bx1, by0);
             deposit_tile<D0>(tile, lx, ly, bx0, by0, wv);
         } else {
             const V3 bb = slow(p.x[0], p.x[1], P);
@@ -369,7 +386,7 @@ struct Op2HEHp3 {
 
     static __device__ __forceinline__ void apply(Part2 &p, const PP &P, const double *ft, double *tile, int bx, int by)
     {
-        constexpr int D1 = D0 - 1, W = Tile<D0>::W, WW = W * W;
+        constexpr int D1 = D0 - 1, W = Tile<D0>::W, WS = Tile<D0>::WS, FS = Tile<D0>::FS;
         int cx, cy;
         double tx, ty;
         locate2<0>(p.x[0], P.m, cx, tx);
@@ -380,13 +397,13 @@ struct Op2HEHp3 {
             basis_pp<D0>(tx, bx0); basis_pp<D1>(tx, bx1);
             basis_pp<D0>(ty, by0); basis_pp<D1>(ty, by1);
             const int lx = rx + kR2, ly = ry + kR2;
-            const double *q = ft + ly * W + lx;
-            p.v[0] += eval_tile<D1, D0, W>(q + 1, bx1, by0);
-            p.v[1] += eval_tile<D0, D1, W>(q + WW + W, bx0, by1);
-            p.v[2] += eval_tile<D0, D0, W>(q + 2 * WW, bx0, by0);
+            const double *q = ft + ly * WS + lx;
+            p.v[0] += eval_tile<D1, D0, WS>(q + 1, bx1, by0);
+            p.v[1] += eval_tile<D0, D1, WS>(q + FS + WS, bx0, by1);
+            p.v[2] += eval_tile<D0, D0, WS>(q + 2 * FS, bx0, by0);
             const double v3 = p.v[2];
-            const double B1 = eval_tile<D0, D1, W>(q + 3 * WW + W, bx0, by1);
-            const double B2 = eval_tile<D1, D0, W>(q + 4 * WW + 1, bx1, by0);
+            const double B1 = eval_tile<D0, D1, WS>(q + 3 * FS + WS, bx0, by1);
+            const double B2 = eval_tile<D1, D0, WS>(q + 4 * FS + 1, bx1, by0);
             p.v[0] = fma(-(P.op.dtqm * v3), B2, p.v[0]);
             p.v[1] = fma(P.op.dtqm * v3, B1, p.v[1]);
             deposit_tile<D0>(tile, lx, ly, bx0, by0, (p.w * P.op.wscale_dt) * v3);
@@ -461,7 +478,7 @@ struct Op2Hp12 {
 
     static __device__ __forceinline__ void apply(Part2 &p, const PP &P, const double *ft, double *tile, int bx, int by)
     {
-        constexpr int D1 = D0 - 1, O = 1 - DIR, W = Tile<D0>::W, WW = W * W;
+        constexpr int D1 = D0 - 1, O = 1 - DIR, W = Tile<D0>::W, WS = Tile<D0>::WS, FS = Tile<D0>::FS;
         const Mesh2 &m = P.m;
         const double x_old = p.x[DIR], x_new = fma(P.op.dt, p.v[DIR], x_old);
         int co, cn, ct;
@@ -494,19 +511,20 @@ struct Op2Hp12 {
                 win[k] = (n1 ? nn : n0) - (o1 ? oo : o0);
             }
             const int lw = rmin + kR2 + (D0 - D1), lt = rt + kR2;
-            // strides of the tile along / across DIR
+            // strides along / across DIR of the deposit tile (sd, st) and of the field tiles (fd, ft_)
             constexpr int sd = DIR == 0 ? 1 : W, st = DIR == 0 ? W : 1;
-            const double *q3 = ft + lw * sd + (lt + 1) * st;        // B3: transverse degree D1
-            const double *qo = ft + WW + lw * sd + lt * st;          // B2 / B1: transverse degree D0
+            constexpr int fd = DIR == 0 ? 1 : WS, ft_ = DIR == 0 ? WS : 1;
+            const double *q3 = ft + lw * fd + (lt + 1) * ft_;        // B3: transverse degree D1
+            const double *qo = ft + FS + lw * fd + lt * ft_;          // B2 / B1: transverse degree D0
             sum_z = 0.0;
             sum_o = 0.0;
 #pragma unroll
             for (int k = 0; k <= D1 + 1; ++k) {
-                double sz = q3[k * sd] * bt1[0], so = qo[k * sd] * bt0[0];
+                double sz = q3[k * fd] * bt1[0], so = qo[k * fd] * bt0[0];
 #pragma unroll
-                for (int b = 1; b <= D1; ++b) sz = fma(q3[k * sd + b * st], bt1[b], sz);
+                for (int b = 1; b <= D1; ++b) sz = fma(q3[k * fd + b * ft_], bt1[b], sz);
 #pragma unroll
-                for (int b = 1; b <= D0; ++b) so = fma(qo[k * sd + b * st], bt0[b], so);
+                for (int b = 1; b <= D0; ++b) so = fma(qo[k * fd + b * ft_], bt0[b], so);
                 sum_z = fma(sz, win[k], sum_z);
                 sum_o = fma(so, win[k], sum_o);
             }
@@ -568,17 +586,17 @@ __device__ __forceinline__ void store2(const Rows2 &r, int64_t i, const Part2 &p
 template <class Op>
 constexpr size_t warp_smem_doubles()
 {
-    return (size_t)Op::NF * Tile<Op::D>::SLOTS + (Op::DEPOSIT ? (size_t)Tile<Op::D>::SLOTS * 32 : 0);
+    return (size_t)Op::NF * Tile<Op::D>::FS + (Op::DEPOSIT ? (size_t)Tile<Op::D>::SLOTS * 32 : 0);
 }
 
 template <class Op>
 __global__ void __launch_bounds__(kThreads2, 3) k2_pass(const __grid_constant__ P2<Op> P)
 {
     extern __shared__ double smem[];
-    constexpr int SLOTS = Tile<Op::D>::SLOTS, W = Tile<Op::D>::W;
+    constexpr int SLOTS = Tile<Op::D>::SLOTS, W = Tile<Op::D>::W, WS = Tile<Op::D>::WS, FS = Tile<Op::D>::FS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *ftile = smem + (size_t)warp * warp_smem_doubles<Op>();
-    double *wtile = ftile + (size_t)Op::NF * SLOTS;
+    double *wtile = ftile + (size_t)Op::NF * FS;
     double *tile = wtile + lane;
     const int nx = P.m.n[0], ny = P.m.n[1];
     const int64_t n_chunks = (P.n + P.chunk - 1) / P.chunk;
@@ -609,7 +627,7 @@ __global__ void __launch_bounds__(kThreads2, 3) k2_pass(const __grid_constant__ 
             const int ly = s / W, lx = s - ly * W;
             const size_t g = (size_t)wrapi(ox + lx, nx) + (size_t)wrapi(oy + ly, ny) * nx;
 #pragma unroll
-            for (int f = 0; f < Op::NF; ++f) ftile[f * SLOTS + s] = Op::stage(P, f, g);
+            for (int f = 0; f < Op::NF; ++f) ftile[f * FS + ly * WS + lx] = Op::stage(P, f, g);
         }
         if (Op::DEPOSIT)
             for (int s = 0; s < SLOTS; ++s) tile[s * 32] = 0.0;
