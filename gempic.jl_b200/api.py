@@ -19,7 +19,7 @@ __all__ = [
     "staggering", "operatorHp1", "operatorHp2", "operatorHE", "operatorHB", "solve_poisson", "write_step",
     "add_charge", "evaluate", "add_current_update_v", "compute_e_from_rho", "compute_e_from_j", "compute_e_from_b",
     "compute_b_from_e", "inner_product", "l2norm_squared", "l2projection", "compute_rhs_from_function",
-    "synchronize", "launch_count", "stream_ptr", "device_info", "set_option", "DIAG_COLUMNS",
+    "synchronize", "launch_count", "stream_ptr", "device_info", "set_option", "DIAG_COLUMNS", "save", "load_particles",
 ]
 
 SMOOTHING = {"collocation": 0, "galerkin": 1}
@@ -784,6 +784,26 @@ def operatorHE(h, dt):
 
 def operatorHB(h, dt):
     h.operatorHB(dt)
+
+
+def save(file, step, p, **fields):
+    """save(file, step, p::ParticleGroup) (src/particle_group.jl:152-165): particle dump "<file>-<step %06d>" with the
+    reference's three entries "x" (D x N), "v" (V x N), "w" (W x N), read back from the device rows (a pending HE kick
+    is applied first).  The container is .npz -- JLD2 needs Julia; the Julia shim writes the reference's .jld2 from the
+    same download.  Extra keyword arrays (e1=..., b=...) are stored alongside, which makes the file a restart point."""
+    D, V = p.dims
+    a = p.to_host()
+    datafile = "%s-%06d.npz" % (file, step)
+    np.savez(datafile, x=a[:D], v=a[D:D + V], w=a[D + V:], **{k: np.asarray(v) for k, v in fields.items()})
+    return datafile
+
+
+def load_particles(file, step, p):
+    """restart from a `save` dump: uploads x, v, w into the device rows of `p`, returns the extra field arrays"""
+    D, V = p.dims
+    with np.load("%s-%06d.npz" % (file, step)) as z:
+        p.upload(np.concatenate([z["x"], z["v"], z["w"]], axis=0))
+        return {k: z[k].copy() for k in z.files if k not in ("x", "v", "w")}
 
 
 def solve_poisson(efield_dofs, particle_group, kernel_smoother_0, maxwell_solver, rho):

@@ -150,6 +150,22 @@ __global__ void k_sort_scan(int *__restrict__ counts, int64_t total)
     }
 }
 
+// particle i of src -> slot d of dst, all rows: every row load is issued before the first store, so a thread keeps
+// `rows` loads in flight instead of one (the scatter is latency bound otherwise: 2048 threads/SM x 8 B)
+constexpr int kMaxRows = 8;
+__device__ __forceinline__ void move_rows(const double *__restrict__ src, double *__restrict__ dst, size_t stride, int rows,
+                                          int64_t i, int64_t d)
+{
+    double v[kMaxRows];
+#pragma unroll
+    for (int r = 0; r < kMaxRows; ++r)
+        if (r < rows) v[r] = src[(size_t)r * stride + i];
+#pragma unroll
+    for (int r = 0; r < kMaxRows; ++r)
+        if (r < rows) dst[(size_t)r * stride + d] = v[r];
+    for (int r = kMaxRows; r < rows; ++r) dst[(size_t)r * stride + d] = src[(size_t)r * stride + i];
+}
+
 __global__ void k_sort_scatter(const double *__restrict__ src, double *__restrict__ dst, size_t stride, int rows,
                                int64_t n, Mesh1D m, int64_t chunk, int n_chunks, const int *__restrict__ offsets)
 {
@@ -169,7 +185,7 @@ __global__ void k_sort_scatter(const double *__restrict__ src, double *__restric
                 const unsigned peers = __match_any_sync(amask, cell);
                 const int rank = __popc(peers & ((1u << lane) - 1u));
                 const int64_t d = (int64_t)mine[cell] + rank;
-                for (int r = 0; r < rows; ++r) dst[(size_t)r * stride + d] = src[(size_t)r * stride + i];
+                move_rows(src, dst, stride, rows, i, d);
                 __syncwarp(amask);
                 if (rank == 0) mine[cell] += __popc(peers);
             }
@@ -279,7 +295,7 @@ __global__ void __launch_bounds__(256) k_sort2_scatter(const double *__restrict_
             if (lane == leader) start = atomicAdd(&sh[cell], __popc(peers));
             start = __shfl_sync(peers, start, leader);
             const int64_t d = (int64_t)start + __popc(peers & ((1u << lane) - 1u));
-            for (int r = 0; r < rows; ++r) dst[(size_t)r * stride + d] = src[(size_t)r * stride + i];
+            move_rows(src, dst, stride, rows, i, d);
         }
     }
 }

@@ -16,7 +16,10 @@ export OneDGrid, TwoDGrid, ParticleGroup, ParticleMeshCoupling1D, Maxwell1DFEM, 
        operatorHp1, operatorHp2, operatorHE, operatorHB, solve_poisson!,
        add_charge!, evaluate, add_current_update_v!, compute_e_from_rho!, compute_e_from_j!,
        compute_e_from_b!, compute_b_from_e!, inner_product, l2norm_squared, l2projection!,
-       compute_rhs_from_function!, write_step!, upload!, download!
+       compute_rhs_from_function!, write_step!, upload!, download!, save, load!
+
+import FileIO            # save / load! write the reference's JLD2 particle dump (GEMPIC.jl depends on FileIO + JLD2)
+using Printf: @sprintf
 
 const LIB = get(ENV, "GEMPIC_B200_LIB", joinpath(@__DIR__, "..", "gempic.jl_b200", "libgempic_b200.so"))
 const Handle = UInt64
@@ -82,6 +85,18 @@ function download!(pg::ParticleGroup)
     size(pg.array, 2) == pg.n_particles || (pg.array = zeros(Float64, sum(pg.dims) + pg.n_weights, pg.n_particles))
     check(ccall((:gempic_pg_download, LIB), Cint, (Handle, Ptr{Cdouble}), pg.handle, pg.array))
     return pg.array
+end
+# save (src/particle_group.jl:152-165): the reference's JLD2 dump, from a fresh download of the device rows
+function save(file, step, p::ParticleGroup{D,V}) where {D,V}
+    a = download!(p)
+    datafile = @sprintf("%s-%06d.jld2", file, step)
+    FileIO.save(datafile, Dict("x" => a[1:D, :], "v" => a[(D + 1):(D + V), :], "w" => a[(D + V + 1):end, :]))
+end
+# restart: fill the device rows from such a dump
+function load!(p::ParticleGroup{D,V}, datafile) where {D,V}
+    d = FileIO.load(datafile)
+    p.array = vcat(d["x"], d["v"], d["w"])
+    upload!(p)
 end
 get_x(p::ParticleGroup{D,V}, i::Int) where {D,V} = p.array[1:D, i]
 get_v(p::ParticleGroup{D,V}, i::Int) where {D,V} = p.array[(D + 1):(D + V), i]

@@ -273,6 +273,31 @@ def test_boris_fused_step_cases(orc, gp, nx, deg0, deg1, sigma1):
         assert rel_err(bg.j_dofs[k], bo.j_dofs[k]) < 1e-11
 
 
+def test_save_and_restart(orc, gp, tmp_path):
+    """save(file, step, p) (particle_group.jl:152-165) from the device rows, and a restart from the dump (taken while a
+    trailing HE kick is pending): the restarted run follows the uninterrupted one.  Not bit for bit -- the uninterrupted
+    run applies the two HE half kicks around the dump as one combined kick, the restarted one as two."""
+    n = 20_000
+    state = weibel_state(n, L_WEIBEL, seed=9)
+    sa, sb = Sim1D(gp, state, L_WEIBEL).init_fields(), Sim1D(gp, state, L_WEIBEL).init_fields()
+    ha, hb = sa.splitting(), sb.splitting()
+    ha.set_fusion(True), hb.set_fusion(True)
+    ha.strang_splitting(0.05, 5)
+    hb.strang_splitting(0.05, 3)
+    f = gp.save(str(tmp_path / "particles"), 3, sb.pg, e1=sb.e1, e2=sb.e2, b=sb.b)
+    with np.load(f) as z:
+        assert z["x"].shape == (1, n) and z["v"].shape == (2, n) and z["w"].shape == (1, n)
+    sc = Sim1D(gp, np.zeros_like(state), L_WEIBEL)
+    fields = gp.load_particles(str(tmp_path / "particles"), 3, sc.pg)
+    sc.e1[:], sc.e2[:], sc.b[:] = fields["e1"], fields["e2"], fields["b"]
+    hc = sc.splitting()
+    hc.set_fusion(True)
+    hc.strang_splitting(0.05, 2)
+    assert particle_err(sc.particles(), sa.particles(), L_WEIBEL) < 1e-12
+    for name in ("e1", "e2", "b"):
+        assert rel_err(getattr(sc, name), getattr(sa, name)) < 1e-12, name
+
+
 def test_diagnostics_write_step(orc, gp):
     n = 50_000
     state = weibel_state(n, L_WEIBEL, seed=2)
