@@ -62,6 +62,7 @@ WORKLOADS["2d3v"] = dict(name="2d3v HamiltonianSplitting with TwoDMaxwell, 64x64
 NX2 = 64
 # 2d3v rows x1,x2,v1,v2,v3,w: HE 40 R + 24 W, Hp3 48 R + 16 W, Hp1/Hp2 48 R + 24 W; sort 2 x 48 + keys
 BYTES2 = {"fused[HE,Hp3]{2,3}": 72, "fused[HE,HE,Hp3]{2,3}": 72, "operatorHE{2,3}": 64, "operatorHp3{2,3}": 64, "operatorHp1{2,3}": 72, "operatorHp2{2,3}": 72, "cell sort 2d": 112,
+          "operatorHp2{2,3}+sort": 96, "cell histogram after Hp2": 24,
           "strang_step": 2 * 64 + 2 * 64 + 3 * 72}
 # algorithmic DRAM bytes per particle of each pass (fp64 SoA rows x, v1, v2, w; SURVEY section 8d / DESIGN.md)
 BYTES = {"operatorHE": 40, "operatorHp2": 40, "operatorHp1": 48, "strang_step": 208,
@@ -320,7 +321,7 @@ def run_ours_2d(args):
 
     if dc.rank == 0:
         peak, peak_src = peaks()
-        passes = {k: v for k, v in prof.items() if k in BYTES2 and k != "cell sort 2d"}
+        passes = {k: v for k, v in prof.items() if k in BYTES2 and k not in ("cell sort 2d", "cell histogram after Hp2")}
         dom = max(passes, key=lambda k: passes[k][0]) if passes else None
         roof = None
         if dom:

@@ -67,6 +67,7 @@ int gempic_pg_set_row_device(gempic_handle h, int row, const double *dev_src)
     require_init();
     ParticleGroup *pg = get_pg(h);
     GP_REQUIRE(row >= 0 && row < pg->rows() && dev_src, GEMPIC_EINVAL, "bad row %d", row);
+    pg->sorted2d = false;
     GP_CUDA(cudaMemcpyAsync(pg->row(row), dev_src, sizeof(double) * pg->n, cudaMemcpyDeviceToDevice, ctx().stream));
     GP_CUDA(cudaStreamSynchronize(ctx().stream));
     GP_API_END

@@ -121,8 +121,29 @@ struct P2 {
     Mesh2 m;
     const double *f[8];
     double *grid;   // deposit target (nx*ny), zeroed by the launcher
+    Rows2 dst;      // Op::SCATTER: the rows of the other particle buffer
+    int *cursor;    // Op::SCATTER: next free slot of every cell (exclusive scan of the histogram of the cells after the push)
     typename Op::Params op;
 };
+
+// Cell-sort key of a position, and the position an operatorHp2 push of dt leaves a particle at.  The histogram kernel
+// and the scattering pass must agree on these bit for bit (a particle counted in one cell and placed in another would
+// overrun a neighbour's range), so both call exactly these functions.
+__device__ __forceinline__ int sort_key2(double x, double y, const Mesh2 &m)
+{
+    int cx = __double2int_rd((x - m.xmin[0]) * m.inv_d[0]), cy = __double2int_rd((y - m.xmin[1]) * m.inv_d[1]);
+    cx = min(max(cx, 0), m.n[0] - 1);
+    cy = min(max(cy, 0), m.n[1] - 1);
+    return cx + cy * m.n[0];
+}
+template <int DIR>
+__device__ __forceinline__ double pushed(double x_old, double v, double dt, const Mesh2 &m)
+{
+    double xw = fma(dt, v, x_old);
+    while (xw < m.xmin[DIR]) xw += m.L[DIR];
+    while (xw >= m.xmax[DIR]) xw -= m.L[DIR];
+    return xw;
+}
 
 // Window of a warp: cells base-R .. base+R in both directions; dofs base-R-D0 .. base+R, i.e. W x W with
 //   local dof index = (cell - base) + R + (D0 - degree) + k,  k = 0..degree.
@@ -170,7 +191,7 @@ struct V3 { double v0, v1, v2; };
 template <int D0>
 struct Op2HE {
     static __device__ __forceinline__ double stage(const P2<Op2HE> &P, int f, size_t g) { return P.f[f][g]; }
-    static constexpr bool DEPOSIT = false, WRITE_X = false, WRITE_V = true;
+    static constexpr bool DEPOSIT = false, WRITE_X = false, WRITE_V = true, SCATTER = false;
     static constexpr int D = D0, NF = 3;
     struct Params { double dtqm; };
     using PP = P2<Op2HE>;
@@ -251,7 +272,7 @@ __device__ __noinline__ void deposit_global(double *__restrict__ grid, int nx, i
 template <int D0>
 struct Op2Charge {
     static __device__ __forceinline__ double stage(const P2<Op2Charge> &P, int f, size_t g) { return P.f[f][g]; }
-    static constexpr bool DEPOSIT = true, WRITE_X = false, WRITE_V = false;
+    static constexpr bool DEPOSIT = true, WRITE_X = false, WRITE_V = false, SCATTER = false;
     static constexpr int D = D0, NF = 0;
     struct Params { double wscale; };
     static __device__ __forceinline__ void apply(Part2 &p, const P2<Op2Charge> &P, const double *, double *tile, int bx, int by)
@@ -277,7 +298,7 @@ struct Op2Charge {
 template <int D0>
 struct Op2Hp3 {
     static __device__ __forceinline__ double stage(const P2<Op2Hp3> &P, int f, size_t g) { return P.f[f][g]; }
-    static constexpr bool DEPOSIT = true, WRITE_X = false, WRITE_V = true;
+    static constexpr bool DEPOSIT = true, WRITE_X = false, WRITE_V = true, SCATTER = false;
     static constexpr int D = D0, NF = 2;
     struct Params { double dtqm, wscale_dt; };
     using PP = P2<Op2Hp3>;
@@ -335,7 +356,7 @@ struct Op2Hp3 {
 //   staged tiles : E1 E2 E3 B1 B2
 template <int D0, int NHE>
 struct Op2HEHp3 {
-    static constexpr bool DEPOSIT = true, WRITE_X = false, WRITE_V = true;
+    static constexpr bool DEPOSIT = true, WRITE_X = false, WRITE_V = true, SCATTER = false;
     static constexpr int D = D0, NF = 5;
     struct Params { double dtqm_e[2], dtqm, wscale_dt; };
     using PP = P2<Op2HEHp3>;
@@ -425,10 +446,18 @@ struct Op2HEHp3 {
 // f[0] = B3, f[1] = B2 (DIR 0) or B1 (DIR 1).  Along DIR the degree-(p-1) splines are integrated over the
 // straight path x_old -> x_new (primitive form, splines.cuh prim_pp; window of p+1 dofs from the lower cell
 // as in OpStrangFused); across DIR the degree-p (j, B2/B1) and degree-(p-1) (B3) splines are evaluated.
-template <int D0, int DIR>
+// SORT: the pass writes every particle (all rows) to its cell-sorted place in the other buffer instead of updating it in
+// place -- the periodic cell sort rides in the last push of a Strang step (k2_pass, sorting_hp2).
+template <int D0, int DIR, bool SORT = false>
 struct Op2Hp12 {
     static __device__ __forceinline__ double stage(const P2<Op2Hp12> &P, int f, size_t g) { return P.f[f][g]; }
-    static constexpr bool DEPOSIT = true, WRITE_X = true, WRITE_V = true;
+    static constexpr bool DEPOSIT = true, WRITE_X = true, WRITE_V = true, SCATTER = SORT;
+    // cell-sort key of the particle after this push (SCATTER)
+    static __device__ __forceinline__ int key_after(const Part2 &p, const P2<Op2Hp12> &P)
+    {
+        const double xn = pushed<DIR>(p.x[DIR], p.v[DIR], P.op.dt, P.m);
+        return DIR == 0 ? sort_key2(xn, p.x[1], P.m) : sort_key2(p.x[0], xn, P.m);
+    }
     static constexpr int D = D0, NF = 2;
     struct Params { double dt, qm_h, wscale_h; };   // h = d[DIR]
     using PP = P2<Op2Hp12>;
@@ -550,10 +579,7 @@ struct Op2Hp12 {
             p.v[0] = fma(P.op.qm_h, sum_z, p.v[0]);
             p.v[2] = fma(-P.op.qm_h, sum_o, p.v[2]);
         }
-        double xw = x_new;
-        while (xw < m.xmin[DIR]) xw += m.L[DIR];
-        while (xw >= m.xmax[DIR]) xw -= m.L[DIR];
-        p.x[DIR] = xw;
+        p.x[DIR] = pushed<DIR>(x_old, p.v[DIR], P.op.dt, m);   // v[DIR] is not changed by this operator
     }
 };
 
@@ -578,6 +604,58 @@ __device__ __forceinline__ void store2(const Rows2 &r, int64_t i, const Part2 &p
         r.v[0][i] = p.v[0];
         r.v[1][i] = p.v[1];
         r.v[2][i] = p.v[2];
+    }
+}
+
+// all rows of a particle to slot d of the other buffer (Op::SCATTER)
+__device__ __forceinline__ void store2_at(const Rows2 &r, int64_t d, const Part2 &p)
+{
+    r.x[0][d] = p.x[0];
+    r.x[1][d] = p.x[1];
+    r.v[0][d] = p.v[0];
+    r.v[1][d] = p.v[1];
+    r.v[2][d] = p.v[2];
+    r.w[d] = p.w;
+}
+// slots for the particles of a warp: one cursor reservation per distinct key (key < 0: lane without a particle).
+// Must be called by all 32 lanes.
+__device__ __forceinline__ int64_t reserve_slot(int *__restrict__ cursor, int key, int lane)
+{
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    int start = 0;
+    if (lane == leader && key >= 0) start = atomicAdd(cursor + key, __popc(peers));
+    start = __shfl_sync(0xffffffffu, start, leader);
+    return (int64_t)start + __popc(peers & ((1u << lane) - 1u));
+}
+
+// histogram of the cell-sort keys the particles will have after an operatorHp2 push of dt (the scattering pass reserves
+// its slots from the exclusive scan of it).  Warp-aggregated shared counters per block, non-zero bins added to `hist`.
+__global__ void __launch_bounds__(256) k2_hist_after_hp2(Rows2 r, int64_t n, double dt, Mesh2 m, int ncell, int *__restrict__ hist)
+{
+    extern __shared__ int shist[];
+    for (int i = threadIdx.x; i < ncell; i += 256) shist[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t per_block = ((n + gridDim.x - 1) / gridDim.x + 255) / 256 * 256;
+    const int64_t lo = (int64_t)blockIdx.x * per_block, hi = min(n, lo + per_block);
+    for (int64_t base = lo + (threadIdx.x & ~31); base < hi; base += 512) {
+        // two batches per iteration: both sets of loads are issued before the first key is needed
+        const int64_t i0 = base + lane, i1 = base + 256 + lane;
+        const bool a0 = i0 < hi, a1 = i1 < hi;
+        double x0 = 0, y0 = 0, v0 = 0, x1 = 0, y1 = 0, v1 = 0;
+        if (a0) { x0 = r.x[0][i0]; y0 = r.x[1][i0]; v0 = r.v[1][i0]; }
+        if (a1) { x1 = r.x[0][i1]; y1 = r.x[1][i1]; v1 = r.v[1][i1]; }
+        const int k0 = a0 ? sort_key2(x0, pushed<1>(y0, v0, dt, m), m) : -1;
+        const int k1 = a1 ? sort_key2(x1, pushed<1>(y1, v1, dt, m), m) : -1;
+        const unsigned p0 = __match_any_sync(0xffffffffu, k0), p1 = __match_any_sync(0xffffffffu, k1);
+        if (a0 && (p0 & ((1u << lane) - 1u)) == 0) atomicAdd(&shist[k0], __popc(p0));
+        if (a1 && (p1 & ((1u << lane) - 1u)) == 0) atomicAdd(&shist[k1], __popc(p1));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ncell; i += 256) {
+        const int c = shist[i];
+        if (c) atomicAdd(&hist[i], c);
     }
 }
 
@@ -637,6 +715,31 @@ __global__ void __launch_bounds__(kThreads2, 3) k2_pass(const __grid_constant__ 
         bool ha = i < hi, hb = i + 32 < hi;
         if (ha) load2<Op>(P.r, i, a);
         if (hb) load2<Op>(P.r, i + 32, b);
+        if constexpr (Op::SCATTER) {
+            // same stream, but every particle goes to its cell-sorted place in the other buffer.  The trip count is warp
+            // uniform (reserve_slot synchronises the warp); the slots are reserved before the arithmetic of the pair, so
+            // the round trip of the cursor atomics is hidden behind it.
+            for (int64_t base = lo; base < hi; base += 64) {
+                const int64_t ni = i + 64;
+                const bool hc = ni < hi, hd = ni + 32 < hi;
+                Part2 c, d;
+                if (hc) load2<Op>(P.r, ni, c);
+                if (hd) load2<Op>(P.r, ni + 32, d);
+                const int64_t da = reserve_slot(P.cursor, ha ? Op::key_after(a, P) : -1, lane);
+                const int64_t db = reserve_slot(P.cursor, hb ? Op::key_after(b, P) : -1, lane);
+                if (ha) {
+                    Op::apply(a, P, ftile, tile, bx, by);
+                    store2_at(P.dst, da, a);
+                }
+                if (hb) {
+                    Op::apply(b, P, ftile, tile, bx, by);
+                    store2_at(P.dst, db, b);
+                }
+                a = c; b = d;
+                ha = hc; hb = hd;
+                i = ni;
+            }
+        } else
         while (ha) {
             const int64_t ni = i + 64;
             const bool hc = ni < hi, hd = ni + 32 < hi;
@@ -823,8 +926,64 @@ static void op2_Hp12(Splitting2D &h, double dt)
     m2d_e_from_j(*h.maxwell, h.e(DIR), h.j(DIR), DIR + 1);
 }
 
+// operatorHp2 that leaves the particles cell sorted: histogram of the cells after the push -> scan -> the push pass
+// places every particle (all rows) at its sorted position in the other buffer -> swap.  24 + 96 B/particle instead of
+// 72 (push in place) + 112 (stand-alone sort).
+static void sorting_hp2(Splitting2D &h, double dt)
+{
+    Context &c = ctx();
+    ParticleGroup &pg = *h.pg;
+    const int cells = (int)h.nd;
+    zero_grid(h.j(1), h.nd);
+    if (pg.sort_keys.n < (size_t)cells) pg.sort_keys.alloc(cells);
+    if (pg.sort_tmp.n < pg.data.n) pg.sort_tmp.alloc(pg.data.n);
+    int *hist = pg.sort_keys.p;
+    GP_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * cells, c.stream));
+    const Mesh2 m = mesh2(*h.maxwell);
+    static bool configured = false;
+    const size_t hsmem = (size_t)cells * sizeof(int);
+    if (!configured && hsmem > 48 * 1024) {
+        GP_CUDA(cudaFuncSetAttribute(k2_hist_after_hp2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+        configured = true;
+    }
+    profile_begin("cell histogram after Hp2");
+    const int hgrid = (int)std::min<int64_t>((int64_t)c.sm_count * 8, (pg.n + 255) / 256);
+    k2_hist_after_hp2<<<hgrid, 256, hsmem, c.stream>>>(rows2(pg), pg.n, dt, m, cells, hist);
+    GP_CUDA(cudaGetLastError());
+    profile_end("cell histogram after Hp2");
+    count_launch();
+    sort_scan(hist, cells);
+    // rows of the other buffer
+    Rows2 dst;
+    {
+        double *base = pg.sort_tmp.p;
+        dst.x[0] = base; dst.x[1] = base + pg.stride;
+        dst.v[0] = base + 2 * pg.stride; dst.v[1] = base + 3 * pg.stride; dst.v[2] = base + 4 * pg.stride;
+        dst.w = base + 5 * pg.stride;
+    }
+    GP_DISPATCH_D0(h.maxwell->s_deg_0, {
+        P2<Op2Hp12<D0, 1, true>> P{};
+        P.f[0] = h.b(2);
+        P.f[1] = h.b(0);
+        P.grid = h.j(1);
+        P.dst = dst;
+        P.cursor = hist;
+        P.op.dt = dt;
+        P.op.qm_h = h.pg->q_over_m * h.maxwell->dy;
+        P.op.wscale_h = h.pg->charge * h.pg->common_weight * h.maxwell->dy;
+        launch2(h, P, "operatorHp2{2,3}+sort");
+    });
+    std::swap(pg.data.p, pg.sort_tmp.p);
+    std::swap(pg.data.n, pg.sort_tmp.n);
+    pg.generation++;
+    pg.sorted2d = true;
+    allreduce_sum(h.j(1), h.nd);
+    m2d_e_from_j(*h.maxwell, h.e(1), h.j(1), 2);
+}
+
 void hs2d_operator(Splitting2D &h, int op, double dt)
 {
+    if (op == GEMPIC_OP_HP1 || op == GEMPIC_OP_HP2) h.pg->sorted2d = false;
     switch (op) {
     case GEMPIC_OP_HP1: op2_Hp12<0>(h, dt); break;
     case GEMPIC_OP_HP2: op2_Hp12<1>(h, dt); break;
@@ -875,8 +1034,15 @@ static void strang2d_fused(Splitting2D &h, double dt, int64_t steps)
     const Maxwell2D &m = *h.maxwell;
     double *b[3] = {h.b(0), h.b(1), h.b(2)};
     const double *e[3] = {h.e(0), h.e(1), h.e(2)};
+    // sort_interval == 1: the cell sort rides in the last push of every step (sorting_hp2); a stand-alone sort is only
+    // needed when somebody else has moved the particles since
+    const bool ride = h.sort_interval == 1 && h.pg->W == 1 && h.pg->n >= 2;
     for (int64_t s = 0; s < steps; ++s) {
-        if (h.sort_interval > 0 && h.steps_done % h.sort_interval == 0) pg_sort_2d(*h.pg, *h.maxwell);
+        if (ride) {
+            if (!h.pg->sorted2d) pg_sort_2d(*h.pg, *h.maxwell);
+        } else if (h.sort_interval > 0 && h.steps_done % h.sort_interval == 0) {
+            pg_sort_2d(*h.pg, *h.maxwell);
+        }
         if (s == 0) {
             hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);
             m2d_b_from_e(m, b, 0.5 * dt, e);
@@ -891,7 +1057,8 @@ static void strang2d_fused(Splitting2D &h, double dt, int64_t steps)
         }
         hs2d_operator(h, GEMPIC_OP_HP2, 0.5 * dt);
         hs2d_operator(h, GEMPIC_OP_HP1, dt);
-        hs2d_operator(h, GEMPIC_OP_HP2, 0.5 * dt);
+        if (ride) sorting_hp2(h, 0.5 * dt);
+        else hs2d_operator(h, GEMPIC_OP_HP2, 0.5 * dt);
         hs2d_operator(h, GEMPIC_OP_HP3, 0.5 * dt);
         h.steps_done++;
     }

@@ -22,6 +22,7 @@ struct ParticleGroup : Object {
     DevBuf<double> sort_tmp;
     DevBuf<int> sort_keys;    // per-cell counters / cursors of the 2D sort
     uint64_t generation = 0;  // bumped whenever the row pointers change (sort) -> stale graphs
+    bool sorted2d = false;    // rows are in 2D cell order (hs2d.cu keeps them so); cleared by whoever rewrites positions
     ParticleGroup() : Object(kKind) {}
     int rows() const { return D + V + W; }
     double *row(int r) { return data.p + (size_t)r * stride; }
@@ -191,6 +192,7 @@ struct Splitting2D : Object {
 void hs2d_operator(Splitting2D &h, int op, double dt);
 void hs2d_strang(Splitting2D &h, double dt, int64_t steps);
 void pg_sort_2d(ParticleGroup &pg, const Maxwell2D &m);
+void sort_scan(int *counts, int64_t total);   // exclusive prefix sum in place (particles.cu)
 
 // applies a deferred trailing HE kick, if any (hs1d.cu); every entry point that reads or moves particles calls it
 void pg_sync(ParticleGroup &pg);

@@ -47,6 +47,7 @@ static const int64_t kStageParticles = 1 << 22;  // 4 Mi records per staging chu
 void pg_upload(ParticleGroup &pg, const double *aos)
 {
     Context &c = ctx();
+    pg.sorted2d = false;
     const int rows = pg.rows();
     const int64_t chunk = std::min<int64_t>(pg.n, kStageParticles);
     DevBuf<double> stage((size_t)chunk * rows);
@@ -195,8 +196,16 @@ __global__ void k_sort_scatter(const double *__restrict__ src, double *__restric
     }
 }
 
+void sort_scan(int *counts, int64_t total)
+{
+    k_sort_scan<<<1, 1024, 0, ctx().stream>>>(counts, total);
+    GP_CUDA(cudaGetLastError());
+    count_launch();
+}
+
 void pg_sort_1d(ParticleGroup &pg, const Pmc1D &p)
 {
+    pg.sorted2d = false;
     Context &c = ctx();
     if (pg.n < 2) return;
     GP_REQUIRE(pg.n < (int64_t)2147483647, GEMPIC_EINVAL, "sort supports < 2^31 particles per GPU");
@@ -341,6 +350,7 @@ void pg_sort_2d(ParticleGroup &pg, const Maxwell2D &mx)
     std::swap(pg.data.p, pg.sort_tmp.p);
     std::swap(pg.data.n, pg.sort_tmp.n);
     pg.generation++;
+    pg.sorted2d = true;
 }
 
 // ---- synthetic loads -------------------------------------------------------------------------
@@ -406,6 +416,7 @@ void pg_sample(ParticleGroup &pg, int kind, double xmin, double L, double alpha,
                uint64_t seed, int64_t first_index)
 {
     Context &c = ctx();
+    pg.sorted2d = false;
     GP_REQUIRE(kind == 0 || kind == 1, GEMPIC_EINVAL, "unknown sample kind %d", kind);
     GP_REQUIRE(pg.V <= 3, GEMPIC_EINVAL, "at most 3 velocity dimensions");
     SampleParams s{};

@@ -108,8 +108,23 @@ def test_strang_resident_sorted_matches_oracle(gp):
     a, b = hg.particle_group.to_host(), ho.particle_group.array
     ka, kb = np.lexsort((a[1], a[0])), np.lexsort((b[1], b[0]))
     assert np.max(np.abs(a[:, ka] - b[:, kb])) < 1e-9   # chaotic amplification over 3 steps; order must match
-    # the sort really ordered the particles by cell
+    # the sort rides in the last push of every step (sorting_hp2): the particles come back in cell order
     cell = np.floor(a[0] / (4 * np.pi / 16)).astype(int) + 16 * np.floor(a[1] / (4 * np.pi / 16)).astype(int)
+    assert np.all(np.diff(cell) >= 0)
+    # one step per call, with the particles replaced in between (stand-alone sort, then the riding one again)
+    st = b.copy()
+    hg.particle_group.upload(st)
+    for _ in range(2):
+        ho.strang_splitting(0.05, 1)
+        hg.strang_splitting(0.05, 1)
+    hg.sync_fields()
+    for c in range(3):
+        assert rel(hg.e_dofs[c], ho.e_dofs[c]) < 1e-10
+    a, b = hg.particle_group.to_host(), ho.particle_group.array
+    ka, kb = np.lexsort((a[1], a[0])), np.lexsort((b[1], b[0]))
+    assert np.max(np.abs(a[:, ka] - b[:, kb])) < 1e-8
+    cell = np.floor(a[0] / (4 * np.pi / 16)).astype(int) + 16 * np.floor(a[1] / (4 * np.pi / 16)).astype(int)
+    assert np.all(np.diff(cell) >= 0)
     hg.particle_group.sort(hg.maxwell_solver)
     a = hg.particle_group.to_host()
     cell = np.floor(a[0] / (4 * np.pi / 16)).astype(int) + 16 * np.floor(a[1] / (4 * np.pi / 16)).astype(int)
