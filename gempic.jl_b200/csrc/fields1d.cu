@@ -38,44 +38,89 @@ __global__ void k_e_from_rho(double *__restrict__ e, const double *__restrict__ 
     for (int i = threadIdx.x; i < n; i += blockDim.x) e[i] = phi[i == 0 ? n - 1 : i - 1] - phi[i];
 }
 
+// The three field updates of a splitting step as block-wide device functions (one block, `sh` = n doubles of shared
+// scratch, callers synchronise before and after), shared by the stand-alone kernels and the fused per-step kernel below
+// so that both perform the same fp64 operations in the same order.
+//
 // compute_e_from_j! (:263-289) with the optional `j .= j .* prescale` that precedes it in
 // operatorHp2 (hamiltonian_splitting_1d2v.jl:173) and Boris (:160-161)
-__global__ void k_e_from_j(double *__restrict__ e, const double *__restrict__ col, double *__restrict__ j, int n,
-                           double dx, double prescale, int do_prescale)
+__device__ __forceinline__ void dev_e_from_j(double *e, const double *__restrict__ col, double *j, int n, double dx,
+                                             double prescale, int do_prescale, double *sh)
 {
-    extern __shared__ double sj[];
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double v = j[i];
         if (do_prescale) {
             v = v * prescale;
             j[i] = v;
         }
-        sj[i] = v;
+        sh[i] = v;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        double work = circ_row(col, sj, i, n);
+        double work = circ_row(col, sh, i, n);
         work = work / dx;
         e[i] = e[i] - work;
     }
-}
-
-// compute_e_from_b! (:384-396)
-__global__ void k_e_from_b(double *__restrict__ e, const double *__restrict__ col, const double *__restrict__ b, int n,
-                           double coef)
-{
-    extern __shared__ double sb[];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sb[i] = b[i];
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) e[i] = e[i] + coef * circ_row(col, sb, i, n);
 }
-
+// compute_e_from_b! (:384-396)
+__device__ __forceinline__ void dev_e_from_b(double *e, const double *__restrict__ col, const double *b, int n, double coef,
+                                             double *sh)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sh[i] = b[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) e[i] = e[i] + coef * circ_row(col, sh, i, n);
+    __syncthreads();
+}
 // compute_b_from_e! (:407-420)
-__global__ void k_b_from_e(double *__restrict__ b, const double *__restrict__ e, int n, double coef)
+__device__ __forceinline__ void dev_b_from_e(double *b, const double *e, int n, double coef)
 {
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const double prev = e[i == 0 ? n - 1 : i - 1];
         b[i] = b[i] + coef * (prev - e[i]);
+    }
+    __syncthreads();
+}
+
+__global__ void k_e_from_j(double *e, const double *__restrict__ col, double *j, int n, double dx, double prescale,
+                           int do_prescale)
+{
+    extern __shared__ double sj[];
+    dev_e_from_j(e, col, j, n, dx, prescale, do_prescale, sj);
+}
+__global__ void k_e_from_b(double *e, const double *__restrict__ col, const double *b, int n, double coef)
+{
+    extern __shared__ double sb[];
+    dev_e_from_b(e, col, b, n, coef, sb);
+}
+__global__ void k_b_from_e(double *b, const double *e, int n, double coef) { dev_b_from_e(b, e, n, coef); }
+
+// Every field-only update between two fused particle passes of strang_splitting! (hs1d.cu strang_fused) in ONE launch
+// instead of nine 3 us ones:
+//   solve   e2 -= M0^-1 (j2 * j2_scale) / dx ; e1 -= M1^-1 j1 / dx ; j_dofs[1] = 0        (Hp2, Hp1, Hp2 of the pass)
+//   tail    eT = (e1, e2) ; b += dt_tail/dx D e2 ; e2 += dt_tail/dx A b                  (trailing HE field part, HB)
+//   lead    e2 += dt_lead/dx A b ; b += dt_lead/dx D e2                                   (leading HB, HE field part)
+__global__ void k_strang_fields(StrangFields F)
+{
+    extern __shared__ double sh[];
+    const int n = F.n;
+    if (F.do_solve) {
+        dev_e_from_j(F.e2, F.inv_mass0, F.acc, n, F.dx, F.j2_scale, F.j2_scale != 1.0 ? 1 : 0, sh);
+        dev_e_from_j(F.e1, F.inv_mass1, F.acc + n, n, F.dx, 1.0, 0, sh);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) F.j1[i] = 0.0;
+    }
+    if (F.do_tail) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            F.eT[i] = F.e1[i];
+            F.eT[n + i] = F.e2[i];
+        }
+        __syncthreads();
+        dev_b_from_e(F.b, F.e2, n, F.dt_tail / F.dx);
+        dev_e_from_b(F.e2, F.ampere, F.b, n, F.dt_tail / F.dx, sh);
+    }
+    if (F.do_lead) {
+        dev_e_from_b(F.e2, F.ampere, F.b, n, F.dt_lead / F.dx, sh);
+        dev_b_from_e(F.b, F.e2, n, F.dt_lead / F.dx);
     }
 }
 
@@ -146,6 +191,18 @@ void field_e_from_j(const Maxwell1D &m, double *e, double *j, int component, dou
     const double *col = m.col(component == 1 ? Maxwell1D::C_INV_MASS1 : Maxwell1D::C_INV_MASS0);
     k_e_from_j<<<1, field_threads(m.n), m.n * sizeof(double), ctx().stream>>>(e, col, j, m.n, m.delta_x, prescale,
                                                                               prescale != 1.0 ? 1 : 0);
+    GP_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+void field_strang_fields(const Maxwell1D &m, StrangFields F)
+{
+    F.inv_mass0 = m.col(Maxwell1D::C_INV_MASS0);
+    F.inv_mass1 = m.col(Maxwell1D::C_INV_MASS1);
+    F.ampere = m.col(Maxwell1D::C_AMPERE);
+    F.n = m.n;
+    F.dx = m.delta_x;
+    k_strang_fields<<<1, field_threads(m.n), m.n * sizeof(double), ctx().stream>>>(F);
     GP_CUDA(cudaGetLastError());
     count_launch();
 }

@@ -127,16 +127,26 @@ static void fused_pass(Splitting &h, double dt, int n_he, double dt_T)
         }
     });
     allreduce_sum(h.acc(), 2 * h.n);
-    const Maxwell1D &m = *h.maxwell;
-    // acc = [j2a + j2b | j1].  compute_e_from_j! is linear and nothing reads e2 between the two Hp2 half steps, so
-    // their two solves (:173-175) collapse into one on the summed current
-    field_e_from_j(m, h.e2(), h.acc(), 2, 0.5 * dt);
-    field_e_from_j(m, h.e1(), h.acc() + h.n, 1, 1.0);            // Hp1         :111
-    // j_dofs as the reference leaves them: the last Hp2 zeroed j1 (:132) and holds dt/2 * j2b -- a deposit of the
-    // particle state this pass leaves behind, rebuilt by materialise_j2() when somebody looks at it
-    GP_CUDA(cudaMemsetAsync(h.j1(), 0, sizeof(double) * h.n, ctx().stream));
+    // The field solves of the pass follow in strang_fields().  j_dofs as the reference leaves them: the last Hp2
+    // zeroed j1 (:132) and holds dt/2 * j2b -- a deposit of the particle state this pass leaves behind, rebuilt by
+    // materialise_j2() when somebody looks at it
     h.j2_stale = true;
     h.j2_scale = 0.5 * dt;
+}
+
+// Field-only updates around the fused pass, one launch (k_strang_fields, fields1d.cu):
+//   solve   acc = [j2a + j2b | j1]: compute_e_from_j! is linear and nothing reads e2 between the two Hp2 half steps, so
+//           their two solves (:173-175) collapse into one on the summed current; then the Hp1 solve (:111); j_dofs[1] = 0
+//   tail    the trailing HE (field part, after a snapshot of e for its particle kick) and HB of a step
+//   lead    the leading HB and HE (field part) of the next step
+static void strang_fields(Splitting &h, bool solve, double dt, bool tail, double dt_tail, bool lead, double dt_lead)
+{
+    StrangFields F{};
+    F.e1 = h.e1(); F.e2 = h.e2(); F.b = h.b(); F.j1 = h.j1(); F.acc = h.acc(); F.eT = h.e1T();   // e1T | e2T adjacent
+    F.do_solve = solve; F.j2_scale = 0.5 * dt;
+    F.do_tail = tail; F.dt_tail = 0.5 * dt_tail;
+    F.do_lead = lead; F.dt_lead = 0.5 * dt_lead;
+    field_strang_fields(*h.maxwell, F);
 }
 
 // j_dofs[2] after a fused pass = dt/2 * sum_p w v2 N(x) over the particles as the pass left them (the second Hp2 of
@@ -194,34 +204,22 @@ static bool fused_fits(Splitting &h)
 // (which the kick does not read), so b is simply advanced before the pass.
 static void strang_fused(Splitting &h, double dt, int64_t steps)
 {
-    const Maxwell1D &m = *h.maxwell;
     ParticleGroup &pg = *h.pg;
     if (pg.pending && pg.pending != &h) pg_sync(pg);
+    // leading HB and HE (field part) of the first step; a pending trailing HE kick of the previous call (fields already
+    // advanced, snapshot in e1T|e2T) rides in the first pass
+    const bool pending = pg.pending != nullptr;
+    pg.pending = nullptr;
+    strang_fields(h, false, dt, false, dt, true, dt);
     for (int64_t s = 0; s < steps; ++s) {
-        if (s == 0 && !pg.pending) {
-            op_HB(h, 0.5 * dt);
-            field_b_from_e(m, h.b(), 0.5 * dt, h.e2());
-            fused_pass(h, dt, 1, dt);
-        } else if (s == 0) {
-            // the previous call left its trailing HE kick pending (fields already advanced, snapshot in e1T|e2T)
-            pg.pending = nullptr;
-            op_HB(h, 0.5 * dt);
-            field_b_from_e(m, h.b(), 0.5 * dt, h.e2());
-            fused_pass(h, dt, 2, h.pending_dt);
-        } else {
-            field_copy(h.e1T(), h.e1(), 2 * h.n);            // e1T|e2T <- e1|e2 (adjacent)
-            field_b_from_e(m, h.b(), 0.5 * dt, h.e2());      // trailing HE of step s-1, field part
-            op_HB(h, 0.5 * dt);                              // trailing HB of step s-1
-            op_HB(h, 0.5 * dt);                              // leading HB of step s
-            field_b_from_e(m, h.b(), 0.5 * dt, h.e2());      // leading HE of step s, field part
-            fused_pass(h, dt, 2, dt);
-        }
+        if (s == 0) fused_pass(h, dt, pending ? 2 : 1, pending ? h.pending_dt : dt);
+        else fused_pass(h, dt, 2, dt);
+        // solves of this pass, trailing HE (field part) + HB of this step, and -- between steps -- the leading HB + HE
+        // of the next one.  The particle kick of the trailing HE only reads the snapshot: it is folded into the next
+        // pass, or deferred to the next call of this splitting / applied by pg_sync() as soon as anybody else touches
+        // the particles
+        strang_fields(h, true, dt, true, dt, s + 1 < steps, dt);
     }
-    // trailing HE + HB: the fields are advanced now; the particle kick (which only reads the snapshot) is deferred
-    // to the next call of this splitting, or applied by pg_sync() as soon as anybody else touches the particles
-    field_copy(h.e1T(), h.e1(), 2 * h.n);
-    field_b_from_e(m, h.b(), 0.5 * dt, h.e2());
-    op_HB(h, 0.5 * dt);
     h.pending_dt = dt;
     pg.pending = &h;
 }

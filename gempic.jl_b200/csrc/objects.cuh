@@ -82,6 +82,16 @@ void field_e_from_rho(const Maxwell1D &m, double *e, const double *rho);
 // j *= prescale (when prescale != 1), then e -= circ(inv_mass, j) / dx   (component 1: mass1, 2: mass0)
 void field_e_from_j(const Maxwell1D &m, double *e, double *j, int component, double prescale);
 void field_e_from_b(const Maxwell1D &m, double *e, double dt, const double *b);
+// all field-only updates between two fused particle passes of strang_splitting! in one launch (fields1d.cu)
+struct StrangFields {
+    double *e1, *e2, *b, *j1, *acc, *eT;   // acc = [j2 | j1] deposits of the fused pass; eT = [e1T | e2T]
+    const double *inv_mass0, *inv_mass1, *ampere;
+    int n;
+    double dx;
+    int do_solve, do_tail, do_lead;
+    double j2_scale, dt_tail, dt_lead;     // dt_* = the (half) time steps of the HE/HB pair
+};
+void field_strang_fields(const Maxwell1D &m, StrangFields F);
 void field_b_from_e(const Maxwell1D &m, double *b, double dt, const double *e);
 // out[0] = sum_i c1[i] * circ(mass_deg, c2)[i] * dx
 void field_inner_product(const Maxwell1D &m, const double *c1, const double *c2, int degree, double *out);
