@@ -71,16 +71,21 @@ void boris_staggering(Boris &s, double dt)   // :99-122
     boris_fields_after_push(s, 0.5 * dt, 0.5 * dt);
 }
 
-static void boris_step(Boris &s, double dt)   // :132-177
+static void boris_fields(Boris &s, bool post, bool pre, double dt)
 {
-    const Maxwell1D &m = *s.maxwell;
-    // (1) b_mid = b ; b += ... ; b_mid = (b_mid + b) * 0.5
-    field_copy(s.f(GEMPIC_F_B_MID), s.f(GEMPIC_F_B), s.n);
-    field_b_from_e(m, s.f(GEMPIC_F_B), dt, s.f(GEMPIC_F_E2_MID));
-    field_axpby(s.f(GEMPIC_F_B_MID), 1.0, s.f(GEMPIC_F_B), 1.0, s.n);   // b_mid + b
-    field_axpby(s.f(GEMPIC_F_B_MID), 0.0, s.f(GEMPIC_F_B), 0.5, s.n);   // (..) * 0.5
-    // (2)+(3) fused particle pass while its lane-private grids and pp tables fit in shared memory (n <~ 40 cells at
-    // degree 3), else the four reference loops one by one
+    BorisFields F{};
+    F.e1 = s.f(GEMPIC_F_E1); F.e2 = s.f(GEMPIC_F_E2); F.b = s.f(GEMPIC_F_B);
+    F.j1 = s.f(GEMPIC_F_J1); F.j2 = s.f(GEMPIC_F_J2);
+    F.e1_mid = s.f(GEMPIC_F_E1_MID); F.e2_mid = s.f(GEMPIC_F_E2_MID); F.b_mid = s.f(GEMPIC_F_B_MID);
+    F.do_post = post; F.do_pre = pre;
+    F.dt_post = F.dt_pre = dt;
+    field_boris_fields(*s.maxwell, F);
+}
+
+// (2)+(3) of a step: the fused particle pass while its lane-private grids and pp tables fit in shared memory
+// (n <~ 40 cells at degree 3), else the four reference loops one by one
+static void boris_particles(Boris &s, double dt)
+{
     bool fused = false;
     GP_DISPATCH_DEGREES(s.ks0->degree, s.ks1->degree, {
         using Op = OpBorisStep<D0, D1>;
@@ -105,14 +110,18 @@ static void boris_step(Boris &s, double dt)   // :132-177
         boris_push_v_epart(s, 0.5 * dt);
         boris_push_x_accumulate_j(s, dt);
     }
-    // (4)
-    field_copy(s.f(GEMPIC_F_E1), s.f(GEMPIC_F_E1_MID), 2 * s.n);
-    boris_fields_after_push(s, dt, dt);
 }
 
+// strang_splitting! :132-177.  Per step: (1) b_mid = b ; b += dt/dx D e2_mid ; b_mid = (b_mid + b)/2, (2)+(3) the particle
+// pass, (4) e = e_mid and the three field solves.  (4) of a step and (1) of the next are one launch (k_boris_fields).
 void boris_strang(Boris &s, double dt, int64_t steps)
 {
-    for (int64_t i = 0; i < steps; ++i) boris_step(s, dt);
+    if (steps <= 0) return;
+    boris_fields(s, false, true, dt);
+    for (int64_t i = 0; i < steps; ++i) {
+        boris_particles(s, dt);
+        boris_fields(s, true, i + 1 < steps, dt);
+    }
 }
 
 }  // namespace gempic

@@ -195,6 +195,44 @@ void field_e_from_j(const Maxwell1D &m, double *e, double *j, int component, dou
     count_launch();
 }
 
+// The field-only part of HamiltonianSplittingBoris.strang_splitting! (hamiltonian_splitting_boris.jl:132-177) around the
+// one-pass particle step, one launch:
+//   post  (4) of the step just pushed: e = e_mid ; e1_mid -= M1^-1 (j1 dt)/dx ; e2_mid += dt/dx A b ; e2_mid -= M0^-1 (j2 dt)/dx
+//   pre   (1) of the next step: b_mid = b ; b += dt/dx D e2_mid ; b_mid = (b_mid + b) * 0.5
+__global__ void k_boris_fields(BorisFields F)
+{
+    extern __shared__ double sh[];
+    const int n = F.n;
+    if (F.do_post) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            F.e1[i] = F.e1_mid[i];
+            F.e2[i] = F.e2_mid[i];
+        }
+        __syncthreads();
+        dev_e_from_j(F.e1_mid, F.inv_mass1, F.j1, n, F.dx, F.dt_post, F.dt_post != 1.0 ? 1 : 0, sh);
+        dev_e_from_b(F.e2_mid, F.ampere, F.b, n, F.dt_post / F.dx, sh);
+        dev_e_from_j(F.e2_mid, F.inv_mass0, F.j2, n, F.dx, F.dt_post, F.dt_post != 1.0 ? 1 : 0, sh);
+    }
+    if (F.do_pre) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) F.b_mid[i] = F.b[i];
+        __syncthreads();
+        dev_b_from_e(F.b, F.e2_mid, n, F.dt_pre / F.dx);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) F.b_mid[i] = (F.b_mid[i] + F.b[i]) * 0.5;
+    }
+}
+
+void field_boris_fields(const Maxwell1D &m, BorisFields F)
+{
+    F.inv_mass0 = m.col(Maxwell1D::C_INV_MASS0);
+    F.inv_mass1 = m.col(Maxwell1D::C_INV_MASS1);
+    F.ampere = m.col(Maxwell1D::C_AMPERE);
+    F.n = m.n;
+    F.dx = m.delta_x;
+    k_boris_fields<<<1, field_threads(m.n), m.n * sizeof(double), ctx().stream>>>(F);
+    GP_CUDA(cudaGetLastError());
+    count_launch();
+}
+
 void field_strang_fields(const Maxwell1D &m, StrangFields F)
 {
     F.inv_mass0 = m.col(Maxwell1D::C_INV_MASS0);

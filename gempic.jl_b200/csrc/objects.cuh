@@ -92,6 +92,16 @@ struct StrangFields {
     double j2_scale, dt_tail, dt_lead;     // dt_* = the (half) time steps of the HE/HB pair
 };
 void field_strang_fields(const Maxwell1D &m, StrangFields F);
+// the same for HamiltonianSplittingBoris: step (4) of the step just pushed and step (1) of the next one
+struct BorisFields {
+    double *e1, *e2, *b, *j1, *j2, *e1_mid, *e2_mid, *b_mid;
+    const double *inv_mass0, *inv_mass1, *ampere;
+    int n;
+    double dx;
+    int do_post, do_pre;
+    double dt_post, dt_pre;
+};
+void field_boris_fields(const Maxwell1D &m, BorisFields F);
 void field_b_from_e(const Maxwell1D &m, double *b, double dt, const double *e);
 // out[0] = sum_i c1[i] * circ(mass_deg, c2)[i] * dx
 void field_inner_product(const Maxwell1D &m, const double *c1, const double *c2, int degree, double *out);
