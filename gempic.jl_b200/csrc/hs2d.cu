@@ -617,16 +617,25 @@ __device__ __forceinline__ void store2_at(const Rows2 &r, int64_t d, const Part2
     r.v[2][d] = p.v[2];
     r.w[d] = p.w;
 }
-// slots for the particles of a warp: one cursor reservation per distinct key (key < 0: lane without a particle).
-// Must be called by all 32 lanes.
-__device__ __forceinline__ int64_t reserve_slot(int *__restrict__ cursor, int key, int lane)
+// Slots for the particles of a warp: one cursor reservation per distinct key (key < 0: lane without a particle), in
+// two halves so that the round trip of the atomic (1-2 us under load) overlaps the particle arithmetic: reserve_begin
+// issues it (the leader keeps the un-consumed result), reserve_end distributes it.  Both are called by all 32 lanes.
+struct Reservation {
+    unsigned peers;
+    int start;
+};
+__device__ __forceinline__ Reservation reserve_begin(int *__restrict__ cursor, int key, int lane)
 {
-    const unsigned peers = __match_any_sync(0xffffffffu, key);
-    const int leader = __ffs(peers) - 1;
-    int start = 0;
-    if (lane == leader && key >= 0) start = atomicAdd(cursor + key, __popc(peers));
-    start = __shfl_sync(0xffffffffu, start, leader);
-    return (int64_t)start + __popc(peers & ((1u << lane) - 1u));
+    Reservation r;
+    r.peers = __match_any_sync(0xffffffffu, key);
+    r.start = 0;
+    if (lane == __ffs(r.peers) - 1 && key >= 0) r.start = atomicAdd(cursor + key, __popc(r.peers));
+    return r;
+}
+__device__ __forceinline__ int64_t reserve_end(const Reservation &r, int lane)
+{
+    const int start = __shfl_sync(0xffffffffu, r.start, __ffs(r.peers) - 1);
+    return (int64_t)start + __popc(r.peers & ((1u << lane) - 1u));
 }
 
 // histogram of the cell-sort keys the particles will have after an operatorHp2 push of dt (the scattering pass reserves
@@ -725,16 +734,13 @@ __global__ void __launch_bounds__(kThreads2, 3) k2_pass(const __grid_constant__ 
                 Part2 c, d;
                 if (hc) load2<Op>(P.r, ni, c);
                 if (hd) load2<Op>(P.r, ni + 32, d);
-                const int64_t da = reserve_slot(P.cursor, ha ? Op::key_after(a, P) : -1, lane);
-                const int64_t db = reserve_slot(P.cursor, hb ? Op::key_after(b, P) : -1, lane);
-                if (ha) {
-                    Op::apply(a, P, ftile, tile, bx, by);
-                    store2_at(P.dst, da, a);
-                }
-                if (hb) {
-                    Op::apply(b, P, ftile, tile, bx, by);
-                    store2_at(P.dst, db, b);
-                }
+                const Reservation ra = reserve_begin(P.cursor, ha ? Op::key_after(a, P) : -1, lane);
+                const Reservation rb = reserve_begin(P.cursor, hb ? Op::key_after(b, P) : -1, lane);
+                if (ha) Op::apply(a, P, ftile, tile, bx, by);
+                if (hb) Op::apply(b, P, ftile, tile, bx, by);
+                const int64_t da = reserve_end(ra, lane), db = reserve_end(rb, lane);
+                if (ha) store2_at(P.dst, da, a);
+                if (hb) store2_at(P.dst, db, b);
                 a = c; b = d;
                 ha = hc; hb = hd;
                 i = ni;
