@@ -468,9 +468,8 @@ int gempic_hs_set_fields(gempic_handle hs, const double *e1, const double *e2, c
     GP_API_BEGIN
     require_init();
     Splitting *h = get<Splitting>(hs, "HamiltonianSplitting");
-    if (e1) h2d(h->e1(), e1, h->n);
-    if (e2) h2d(h->e2(), e2, h->n);
-    if (b) h2d(h->b(), b, h->n);
+    const double *src[3] = {e1, e2, b};
+    h2d_vectors(h->fields.p, src, 3, h->n);   // e1 | e2 | b are adjacent
     GP_API_END
 }
 
@@ -479,13 +478,9 @@ int gempic_hs_get_fields(gempic_handle hs, double *e1, double *e2, double *b, do
     GP_API_BEGIN
     require_init();
     Splitting *h = get<Splitting>(hs, "HamiltonianSplitting");
-    Context &c = ctx();
     if (j2) hs_materialise_j2(*h);
     double *dst[5] = {e1, e2, b, j1, j2};
-    for (int k = 0; k < 5; ++k)
-        if (dst[k])
-            GP_CUDA(cudaMemcpyAsync(dst[k], h->fields.p + (size_t)k * h->n, sizeof(double) * h->n, cudaMemcpyDeviceToHost, c.stream));
-    GP_CUDA(cudaStreamSynchronize(c.stream));
+    d2h_vectors(dst, h->fields.p, 5, h->n);   // e1 | e2 | b | j1 | j2 are adjacent
     GP_API_END
 }
 
@@ -571,9 +566,8 @@ int gempic_boris_set_fields(gempic_handle bs, const double *e1, const double *e2
     require_init();
     Boris *s = get<Boris>(bs, "HamiltonianSplittingBoris");
     pg_sync(*s->pg);
-    if (e1) h2d(s->f(GEMPIC_F_E1), e1, s->n);
-    if (e2) h2d(s->f(GEMPIC_F_E2), e2, s->n);
-    if (b) h2d(s->f(GEMPIC_F_B), b, s->n);
+    const double *src[3] = {e1, e2, b};
+    h2d_vectors(s->f(GEMPIC_F_E1), src, 3, s->n);   // E1 | E2 | B are adjacent
     GP_API_END
 }
 
@@ -616,11 +610,11 @@ int gempic_boris_strang_splitting(gempic_handle bs, double dt, int64_t number_st
 
 static int boris_fields_out(gempic_handle bs, double *e1, double *e2, double *b)
 {
-    int rc = 0;
-    if (e1 && !rc) rc = gempic_boris_get_field(bs, GEMPIC_F_E1, e1);
-    if (e2 && !rc) rc = gempic_boris_get_field(bs, GEMPIC_F_E2, e2);
-    if (b && !rc) rc = gempic_boris_get_field(bs, GEMPIC_F_B, b);
-    return rc;
+    GP_API_BEGIN
+    Boris *s = get<Boris>(bs, "HamiltonianSplittingBoris");
+    double *dst[3] = {e1, e2, b};
+    d2h_vectors(dst, s->f(GEMPIC_F_E1), 3, s->n);
+    GP_API_END
 }
 
 int gempic_boris_staggering_host(gempic_handle bs, double dt, double *e1, double *e2, double *b)

@@ -86,6 +86,9 @@ struct DevBuf {
 
 void h2d(double *dev, const double *host, size_t n);  // synchronous w.r.t. the host buffer
 void d2h(double *host, const double *dev, size_t n);  // synchronises the library stream
+// k back-to-back device vectors of n doubles <-> k host arrays (null entries skipped), one transfer through pinned memory
+void h2d_vectors(double *dev, const double *const *host, int k, size_t n);
+void d2h_vectors(double *const *host, const double *dev, int k, size_t n);   // synchronises the library stream
 
 // ---- objects behind handles -----------------------------------------------------------
 enum class Kind : uint32_t { ParticleGroup = 1, Pmc1D, Pmc2D, Maxwell1D, Splitting, Boris, Maxwell2D, Splitting2D };

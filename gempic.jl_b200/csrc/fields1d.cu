@@ -102,25 +102,62 @@ __global__ void k_b_from_e(double *b, const double *e, int n, double coef) { dev
 //   lead    e2 += dt_lead/dx A b ; b += dt_lead/dx D e2                                   (leading HB, HE field part)
 __global__ void k_strang_fields(StrangFields F)
 {
+    // Everything lives in shared memory between the first load and the final store: the phases below would otherwise be
+    // a chain of ~10 dependent global round trips.  Layout (n doubles each): scratch | e1 | e2 | b | acc (2n) | eT (2n) |
+    // inv_mass0 | inv_mass1 | ampere
     extern __shared__ double sh[];
     const int n = F.n;
+    double *e1 = sh + n, *e2 = e1 + n, *b = e2 + n, *acc = b + n, *eT = acc + 2 * n;
+    double *c0 = eT + 2 * n, *c1 = c0 + n, *ca = c1 + n;
+    if (F.n_partials >= 0) {
+        // acc[g] = sum_b partials[b][g]: one warp per output, the summation order of k_reduce_partials
+        const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+        for (int o = threadIdx.x >> 5; o < F.n_acc; o += nw) {
+            double s = 0.0;
+            for (int k = lane; k < F.n_partials; k += 32) s += F.partials[(size_t)k * F.n_acc + o];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+            if (lane == 0) acc[o] = s;
+        }
+    } else if (F.do_solve) {
+        for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) acc[i] = F.acc[i];
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        e1[i] = F.e1[i];
+        e2[i] = F.e2[i];
+        b[i] = F.b[i];
+        c0[i] = F.inv_mass0[i];
+        c1[i] = F.inv_mass1[i];
+        ca[i] = F.ampere[i];
+    }
+    __syncthreads();
     if (F.do_solve) {
-        dev_e_from_j(F.e2, F.inv_mass0, F.acc, n, F.dx, F.j2_scale, F.j2_scale != 1.0 ? 1 : 0, sh);
-        dev_e_from_j(F.e1, F.inv_mass1, F.acc + n, n, F.dx, 1.0, 0, sh);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) F.j1[i] = 0.0;
+        dev_e_from_j(e2, c0, acc, n, F.dx, F.j2_scale, F.j2_scale != 1.0 ? 1 : 0, sh);
+        dev_e_from_j(e1, c1, acc + n, n, F.dx, 1.0, 0, sh);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            F.j1[i] = 0.0;
+            F.acc[i] = acc[i];           // dt/2 (j2a + j2b), kept for inspection
+            F.acc[n + i] = acc[n + i];
+        }
     }
     if (F.do_tail) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            F.eT[i] = F.e1[i];
-            F.eT[n + i] = F.e2[i];
+            eT[i] = e1[i];
+            eT[n + i] = e2[i];
         }
         __syncthreads();
-        dev_b_from_e(F.b, F.e2, n, F.dt_tail / F.dx);
-        dev_e_from_b(F.e2, F.ampere, F.b, n, F.dt_tail / F.dx, sh);
+        dev_b_from_e(b, e2, n, F.dt_tail / F.dx);
+        dev_e_from_b(e2, ca, b, n, F.dt_tail / F.dx, sh);
+        for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) F.eT[i] = eT[i];
     }
     if (F.do_lead) {
-        dev_e_from_b(F.e2, F.ampere, F.b, n, F.dt_lead / F.dx, sh);
-        dev_b_from_e(F.b, F.e2, n, F.dt_lead / F.dx);
+        dev_e_from_b(e2, ca, b, n, F.dt_lead / F.dx, sh);
+        dev_b_from_e(b, e2, n, F.dt_lead / F.dx);
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        F.e1[i] = e1[i];
+        F.e2[i] = e2[i];
+        F.b[i] = b[i];
     }
 }
 
@@ -240,7 +277,8 @@ void field_strang_fields(const Maxwell1D &m, StrangFields F)
     F.ampere = m.col(Maxwell1D::C_AMPERE);
     F.n = m.n;
     F.dx = m.delta_x;
-    k_strang_fields<<<1, field_threads(m.n), m.n * sizeof(double), ctx().stream>>>(F);
+    const int threads = F.n_partials >= 0 ? 256 : field_threads(m.n);
+    k_strang_fields<<<1, threads, 12 * (size_t)m.n * sizeof(double), ctx().stream>>>(F);
     GP_CUDA(cudaGetLastError());
     count_launch();
 }

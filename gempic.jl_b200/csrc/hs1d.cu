@@ -93,7 +93,7 @@ static void op_Hp1(Splitting &h, double dt, bool with_rho)
 // fused particle pass [HE x n_he, Hp2(dt/2), Hp1(dt), Hp2(dt/2)] + the three field solves.
 // n_he = 1: fields e1,e2 = current.  n_he = 2: the first kick reads the snapshot (e1T, e2T)
 // taken before the trailing HE's field update of the previous step.
-static void fused_pass(Splitting &h, double dt, int n_he, double dt_T)
+static void fused_pass(Splitting &h, double dt, int n_he, double dt_T, DeferredReduce *defer)
 {
     const double qm = h.pg->q_over_m;
     GP_DISPATCH_DEGREES(h.ks0->degree, h.ks1->degree, {
@@ -108,7 +108,7 @@ static void fused_pass(Splitting &h, double dt, int n_he, double dt_T)
             typename OpHp1<D0, D1, false>::Params hp;
             set_hp1_params<OpHp1<D0, D1, false>>(h, dt, hp);
             P.op.dt = hp.dt; P.op.qm_dx = hp.qm_dx; P.op.wscale0 = hp.wscale0; P.op.wscale1_dx = hp.wscale1_dx;
-            launch_pass<Op>(P, &h.scratch, h.acc(), "fused[HE,Hp2,Hp1,Hp2]");
+            launch_pass<Op>(P, &h.scratch, h.acc(), "fused[HE,Hp2,Hp1,Hp2]", defer);
         } else {
             using Op = OpStrangFused<D0, D1, 2>;
             auto P = base_params<Op>(h);
@@ -123,10 +123,10 @@ static void fused_pass(Splitting &h, double dt, int n_he, double dt_T)
             typename OpHp1<D0, D1, false>::Params hp;
             set_hp1_params<OpHp1<D0, D1, false>>(h, dt, hp);
             P.op.dt = hp.dt; P.op.qm_dx = hp.qm_dx; P.op.wscale0 = hp.wscale0; P.op.wscale1_dx = hp.wscale1_dx;
-            launch_pass<Op>(P, &h.scratch, h.acc(), "fused[HE,HE,Hp2,Hp1,Hp2]");
+            launch_pass<Op>(P, &h.scratch, h.acc(), "fused[HE,HE,Hp2,Hp1,Hp2]", defer);
         }
     });
-    allreduce_sum(h.acc(), 2 * h.n);
+    if (!defer) allreduce_sum(h.acc(), 2 * h.n);
     // The field solves of the pass follow in strang_fields().  j_dofs as the reference leaves them: the last Hp2
     // zeroed j1 (:132) and holds dt/2 * j2b -- a deposit of the particle state this pass leaves behind, rebuilt by
     // materialise_j2() when somebody looks at it
@@ -139,9 +139,13 @@ static void fused_pass(Splitting &h, double dt, int n_he, double dt_T)
 //           their two solves (:173-175) collapse into one on the summed current; then the Hp1 solve (:111); j_dofs[1] = 0
 //   tail    the trailing HE (field part, after a snapshot of e for its particle kick) and HB of a step
 //   lead    the leading HB and HE (field part) of the next step
-static void strang_fields(Splitting &h, bool solve, double dt, bool tail, double dt_tail, bool lead, double dt_lead)
+static void strang_fields(Splitting &h, bool solve, double dt, bool tail, double dt_tail, bool lead, double dt_lead,
+                          const DeferredReduce *defer = nullptr)
 {
     StrangFields F{};
+    F.n_partials = defer ? defer->n_blocks : -1;
+    F.partials = defer ? defer->partials : nullptr;
+    F.n_acc = 2 * h.n;
     F.e1 = h.e1(); F.e2 = h.e2(); F.b = h.b(); F.j1 = h.j1(); F.acc = h.acc(); F.eT = h.e1T();   // e1T | e2T adjacent
     F.do_solve = solve; F.j2_scale = 0.5 * dt;
     F.do_tail = tail; F.dt_tail = 0.5 * dt_tail;
@@ -211,14 +215,17 @@ static void strang_fused(Splitting &h, double dt, int64_t steps)
     const bool pending = pg.pending != nullptr;
     pg.pending = nullptr;
     strang_fields(h, false, dt, false, dt, true, dt);
+    // one GPU: the per-block partial sums of the pass are reduced by the field kernel itself (one launch less)
+    const bool single = ctx().n_ranks == 1;
     for (int64_t s = 0; s < steps; ++s) {
-        if (s == 0) fused_pass(h, dt, pending ? 2 : 1, pending ? h.pending_dt : dt);
-        else fused_pass(h, dt, 2, dt);
+        DeferredReduce dr, *defer = single ? &dr : nullptr;
+        if (s == 0) fused_pass(h, dt, pending ? 2 : 1, pending ? h.pending_dt : dt, defer);
+        else fused_pass(h, dt, 2, dt, defer);
         // solves of this pass, trailing HE (field part) + HB of this step, and -- between steps -- the leading HB + HE
         // of the next one.  The particle kick of the trailing HE only reads the snapshot: it is folded into the next
         // pass, or deferred to the next call of this splitting / applied by pg_sync() as soon as anybody else touches
         // the particles
-        strang_fields(h, true, dt, true, dt, s + 1 < steps, dt);
+        strang_fields(h, true, dt, true, dt, s + 1 < steps, dt, defer);
     }
     h.pending_dt = dt;
     pg.pending = &h;

@@ -73,14 +73,21 @@ inline int configure_kernel(size_t smem)
 }
 
 // Launch one pass. For deposit ops the reduced accumulators (n_acc doubles) land in `out`
-// (device) through `scratch`.  `out` may be null for non-deposit ops.
+// (device) through `scratch`.  `out` may be null for non-deposit ops.  With `defer` the per-block partials are left
+// un-reduced for the caller's next kernel (k_strang_fields sums them itself): defer->partials / n_blocks describe them
+// (n_blocks = 0: no particles, the sums are zero).
+struct DeferredReduce {
+    const double *partials = nullptr;
+    int n_blocks = 0;
+};
 template <class Op>
-inline void launch_pass(PassParams<Op> P, PartialScratch *scratch, double *out, const char *tag = nullptr)
+inline void launch_pass(PassParams<Op> P, PartialScratch *scratch, double *out, const char *tag = nullptr,
+                        DeferredReduce *defer = nullptr)
 {
     Context &c = ctx();
     const int n_out = acc_outputs<Op>(P.m.n);
     if (P.n_particles <= 0) {
-        if (Op::DEPOSIT && out) GP_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * n_out, c.stream));
+        if (Op::DEPOSIT && out && !defer) GP_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * n_out, c.stream));
         return;
     }
     LaunchInfo L = plan_pass(P);
@@ -101,7 +108,10 @@ inline void launch_pass(PassParams<Op> P, PartialScratch *scratch, double *out, 
     GP_CUDA(cudaGetLastError());
     if (tag) profile_end(tag);
     count_launch();
-    if (Op::DEPOSIT) {
+    if (Op::DEPOSIT && defer) {
+        defer->partials = P.partials;
+        defer->n_blocks = grid;
+    } else if (Op::DEPOSIT) {
         const int warps_per_block = 4;
         const int blocks = (n_out + warps_per_block - 1) / warps_per_block;
         k_reduce_partials<<<blocks, warps_per_block * 32, 0, c.stream>>>(P.partials, grid, n_out, out);

@@ -90,6 +90,10 @@ struct StrangFields {
     double dx;
     int do_solve, do_tail, do_lead;
     double j2_scale, dt_tail, dt_lead;     // dt_* = the (half) time steps of the HE/HB pair
+    // single GPU: the per-block partial sums of the pass, reduced into acc by this kernel first (n_partials < 0: acc is
+    // already reduced -- and all-reduced -- by the caller)
+    const double *partials;
+    int n_partials, n_acc;
 };
 void field_strang_fields(const Maxwell1D &m, StrangFields F);
 // the same for HamiltonianSplittingBoris: step (4) of the step just pushed and step (1) of the next one

@@ -122,6 +122,62 @@ void h2d(double *dev, const double *host, size_t n)
     }
 }
 
+// k vectors of n doubles that sit back to back on the device <-> k separate host arrays (null = skip), in ONE transfer
+// through the pinned staging buffer: the aliased e_dofs / b_dofs of a drop-in call (3 x 256 B) would otherwise be three
+// pageable copies of ~10 us each way.
+void h2d_vectors(double *dev, const double *const *host, int k, size_t n)
+{
+    Context &c = ctx();
+    const size_t bytes = (size_t)k * n * sizeof(double);
+    bool all = true;
+    for (int i = 0; i < k; ++i) all = all && host[i];
+    if (!all || bytes > kPinnedBytes / 4) {
+        for (int i = 0; i < k; ++i)
+            if (host[i]) h2d(dev + (size_t)i * n, host[i], n);
+        return;
+    }
+    ensure_pinned();
+    if (g_pinned_off + bytes > kPinnedBytes) {
+        GP_CUDA(cudaStreamSynchronize(c.stream));
+        g_pinned_off = 0;
+    }
+    char *p = reinterpret_cast<char *>(c.pinned) + g_pinned_off;
+    for (int i = 0; i < k; ++i) std::memcpy(p + (size_t)i * n * sizeof(double), host[i], n * sizeof(double));
+    GP_CUDA(cudaMemcpyAsync(dev, p, bytes, cudaMemcpyHostToDevice, c.stream));
+    g_pinned_off += (bytes + 255) & ~(size_t)255;
+}
+
+void d2h_vectors(double *const *host, const double *dev, int k, size_t n)
+{
+    Context &c = ctx();
+    int last = -1;
+    for (int i = 0; i < k; ++i)
+        if (host[i]) last = i;
+    if (last < 0) {
+        GP_CUDA(cudaStreamSynchronize(c.stream));
+        return;
+    }
+    const size_t bytes = (size_t)(last + 1) * n * sizeof(double);
+    if (bytes > kPinnedBytes / 4) {
+        for (int i = 0; i <= last; ++i)
+            if (host[i]) GP_CUDA(cudaMemcpyAsync(host[i], dev + (size_t)i * n, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        GP_CUDA(cudaStreamSynchronize(c.stream));
+        return;
+    }
+    ensure_pinned();
+    // the staging buffer is shared with in-flight uploads: drain the stream by reading into a fresh region and waiting
+    if (g_pinned_off + bytes > kPinnedBytes) {
+        GP_CUDA(cudaStreamSynchronize(c.stream));
+        g_pinned_off = 0;
+    }
+    char *p = reinterpret_cast<char *>(c.pinned) + g_pinned_off;
+    GP_CUDA(cudaMemcpyAsync(p, dev, bytes, cudaMemcpyDeviceToHost, c.stream));
+    GP_CUDA(cudaStreamSynchronize(c.stream));
+    for (int i = 0; i <= last; ++i)
+        if (host[i]) std::memcpy(host[i], p + (size_t)i * n * sizeof(double), n * sizeof(double));
+    g_pinned_off = 0;   // everything before the synchronise has been consumed
+}
+
 void d2h(double *host, const double *dev, size_t n)
 {
     Context &c = ctx();
