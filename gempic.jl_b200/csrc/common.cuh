@@ -42,7 +42,6 @@ struct Context {
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
-    bool use_graphs = true;
     // multi-GPU
     void *nccl_comm = nullptr;
     int n_ranks = 1, rank = 0;

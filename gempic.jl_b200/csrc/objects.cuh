@@ -21,7 +21,7 @@ struct ParticleGroup : Object {
     size_t stride = 0;    // row pitch in doubles (multiple of 32 -> 256 B aligned rows)
     DevBuf<double> sort_tmp;
     DevBuf<int> sort_keys;    // per-cell counters / cursors of the 2D sort
-    uint64_t generation = 0;  // bumped whenever the row pointers change (sort) -> stale graphs
+    uint64_t generation = 0;  // bumped whenever the row pointers change (sort)
     bool sorted2d = false;    // rows are in 2D cell order (hs2d.cu keeps them so); cleared by whoever rewrites positions
     ParticleGroup() : Object(kKind) {}
     int rows() const { return D + V + W; }
@@ -160,16 +160,7 @@ struct Splitting : Object {
     bool j2_stale = false;
     double j2_scale = 0.0;
     gempic_handle pg_handle = 0;
-    // CUDA graph of one Strang step, keyed by dt
-    cudaGraphExec_t graph = nullptr;
-    double graph_dt = 0.0;
-    int graph_fuse = -1;
-    uint64_t graph_generation = 0;
     Splitting() : Object(kKind) {}
-    ~Splitting() override
-    {
-        if (graph) cudaGraphExecDestroy(graph);
-    }
     double *e1() { return fields.p; }
     double *e2() { return fields.p + n; }
     double *b() { return fields.p + 2 * (size_t)n; }

@@ -39,16 +39,6 @@ __device__ __forceinline__ double gather_h(const double *__restrict__ field, int
     return v;
 }
 
-// sum_k field[k * S] * b[k]  (field points at the first dof of the stencil, copy stride S)
-template <int D, int S>
-__device__ __forceinline__ double gather_s(const double *__restrict__ field, const double (&b)[D + 1])
-{
-    double v = field[0] * b[0];
-#pragma unroll
-    for (int k = 1; k <= D; ++k) v = fma(field[k * S], b[k], v);
-    return v;
-}
-
 // grid[g0+k] += ws * N_k   with ws = marker charge * scaling   (add_charge!, pmc1d.jl:261-280)
 template <int D, bool LP>
 __device__ __forceinline__ void deposit_h(const Acc<LP> &acc, int slot0, const double (&b)[D + 1], double ws)

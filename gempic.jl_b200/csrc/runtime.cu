@@ -382,8 +382,8 @@ int gempic_set_option(const char *name, int64_t value)
 {
     GP_API_BEGIN
     GP_REQUIRE(name, GEMPIC_EINVAL, "null option name");
-    if (!strcmp(name, "graphs")) ctx().use_graphs = value != 0;
-    else fail(GEMPIC_EINVAL, "unknown option '%s'", name);
+    (void)value;
+    fail(GEMPIC_EINVAL, "unknown option '%s'", name);
     GP_API_END
 }
 

@@ -178,53 +178,4 @@ __device__ __forceinline__ double mod_julia(double x, double L)
     return r;
 }
 
-// sum_k field[(cell-D+k) mod n] * b[k], accumulated from 0.0 in k order (evaluate, :446-450)
-template <int D>
-__device__ __forceinline__ double gather(const double *__restrict__ field, int cell, const double (&b)[D + 1],
-                                         const Mesh1D &m)
-{
-    int g = wrap_index(cell - D, m);
-    double v = 0.0;
-#pragma unroll
-    for (int k = 0; k <= D; ++k) {
-        v += field[g] * b[k];
-        g = wrap_next(g + 1, m.n);
-    }
-    return v;
-}
-
-// Gauss-Legendre nodes on [-1,1] for n_quad = (degree+2)/2 (src/particle_mesh_coupling_1d.jl:67,72)
-template <int D>
-struct Quad {
-    static constexpr int n = (D + 2) / 2;
-};
-__device__ __forceinline__ double quad_x(int nq, int q)
-{
-    // n=1: {0}; n=2: {-1/sqrt(3), +1/sqrt(3)}
-    return nq == 1 ? 0.0 : (q == 0 ? -0.57735026918962576451 : 0.57735026918962576451);
-}
-__device__ __forceinline__ double quad_w(int nq, int /*q*/) { return nq == 1 ? 2.0 : 1.0; }
-
-// Line-integral weights of one in-cell segment [lower, upper] (cell units):
-//   s[k] = sign * dx * sum_q w_q c1 N_k(c1 x_q + c2)      (update_jv!, :399-414)
-template <int D>
-__device__ __forceinline__ void segment_weights(double lower, double upper, double sign_dx, double (&s)[D + 1])
-{
-    constexpr int NQ = Quad<D>::n;
-    const double c1 = 0.5 * (upper - lower);
-    const double c2 = 0.5 * (upper + lower);
-    bspline_basis<D>(c1 * quad_x(NQ, 0) + c2, s);
-    const double f = quad_w(NQ, 0) * c1;
-#pragma unroll
-    for (int k = 0; k <= D; ++k) s[k] *= f;
-    if (NQ > 1) {
-        double more[D + 1];
-        bspline_basis<D>(c1 * quad_x(NQ, 1) + c2, more);
-#pragma unroll
-        for (int k = 0; k <= D; ++k) s[k] += more[k] * quad_w(NQ, 1) * c1;
-    }
-#pragma unroll
-    for (int k = 0; k <= D; ++k) s[k] *= sign_dx;
-}
-
 }  // namespace gempic

@@ -65,7 +65,8 @@ int64_t gempic_launch_count(int reset);
  * name, accumulated milliseconds, launches); it returns 100 past the last slot. */
 int gempic_profile_enable(int on);
 int gempic_profile_read(int slot, char *tag, int tag_len, double *ms, int64_t *launches);
-/* 1: capture strang steps into CUDA graphs (default), 0: plain stream launches. */
+/* Run-time options by name.  None is defined in this version (every name returns GEMPIC_EINVAL); the per-step
+ * launch sequence is already 2-3 kernels, so there is nothing for a CUDA-graph switch to toggle. */
 int gempic_set_option(const char *name, int64_t value);
 
 /* ---- multi-GPU: particles sharded by rank, grid moments all-reduced ------------------
