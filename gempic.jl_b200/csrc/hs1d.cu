@@ -233,6 +233,7 @@ static void strang_fused(Splitting &h, double dt, int64_t steps)
 
 void pg_sync(ParticleGroup &pg)
 {
+    if (pg.pending2d) hs2d_apply_pending(pg);
     Splitting *h = pg.pending;
     if (!h) return;
     pg.pending = nullptr;

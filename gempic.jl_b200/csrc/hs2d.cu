@@ -878,14 +878,20 @@ void hs2d_charge(Splitting2D &h, double *rho_dev)
     allreduce_sum(rho_dev, h.nd);
 }
 
-static void op2_HE(Splitting2D &h, double dt)
+// the particle kick of operatorHE with the given field vectors
+static void op2_HE_particles(Splitting2D &h, double dt, const double *e1, const double *e2, const double *e3)
 {
     GP_DISPATCH_D0(h.maxwell->s_deg_0, {
         P2<Op2HE<D0>> P{};
-        P.f[0] = h.e(0); P.f[1] = h.e(1); P.f[2] = h.e(2);
+        P.f[0] = e1; P.f[1] = e2; P.f[2] = e3;
         P.op.dtqm = dt * h.pg->q_over_m;
         launch2(h, P, "operatorHE{2,3}");
     });
+}
+
+static void op2_HE(Splitting2D &h, double dt)
+{
+    op2_HE_particles(h, dt, h.e(0), h.e(1), h.e(2));
     double *b[3] = {h.b(0), h.b(1), h.b(2)};
     const double *e[3] = {h.e(0), h.e(1), h.e(2)};
     m2d_b_from_e(*h.maxwell, b, dt, e);
@@ -1001,7 +1007,7 @@ void hs2d_operator(Splitting2D &h, int op, double dt)
 }
 
 // [HE x n_he, Hp3](dt/2) in one pass + the e3 solve; n_he = 2 reads the snapshot eT of the trailing HE's field
-static void fused_he_hp3(Splitting2D &h, double dt, int n_he)
+static void fused_he_hp3(Splitting2D &h, double dt, int n_he, double dt_T)
 {
     zero_grid(h.j(2), h.nd);
     const double qm = h.pg->q_over_m;
@@ -1020,7 +1026,8 @@ static void fused_he_hp3(Splitting2D &h, double dt, int n_he)
             for (int c = 0; c < 3; ++c) { P.f[c] = h.e(c); P.f[3 + c] = h.eT(c); }
             P.f[6] = h.b(0); P.f[7] = h.b(1);
             P.grid = h.j(2);
-            P.op.dtqm_e[0] = P.op.dtqm_e[1] = 0.5 * dt * qm;
+            P.op.dtqm_e[0] = 0.5 * dt * qm;
+            P.op.dtqm_e[1] = 0.5 * dt_T * qm;   // trailing HE of the previous step: snapshot fields eT, that step's dt
             P.op.dtqm = 0.5 * dt * qm;
             P.op.wscale_dt = h.pg->charge * h.pg->common_weight * 0.5 * dt;
             launch2(h, P, "fused[HE,HE,Hp3]{2,3}");
@@ -1043,6 +1050,12 @@ static void strang2d_fused(Splitting2D &h, double dt, int64_t steps)
     // sort_interval == 1: the cell sort rides in the last push of every step (sorting_hp2); a stand-alone sort is only
     // needed when somebody else has moved the particles since
     const bool ride = h.sort_interval == 1 && h.pg->W == 1 && h.pg->n >= 2;
+    // a trailing HE kick this splitting left pending in its previous call (fields already advanced, snapshot in eT)
+    // rides in the first pass of this one; anybody else's is applied first
+    ParticleGroup &pg = *h.pg;
+    if (pg.pending || (pg.pending2d && pg.pending2d != &h)) pg_sync(pg);
+    const bool pending = pg.pending2d == &h;
+    pg.pending2d = nullptr;
     for (int64_t s = 0; s < steps; ++s) {
         if (ride) {
             if (!h.pg->sorted2d) pg_sort_2d(*h.pg, *h.maxwell);
@@ -1052,14 +1065,14 @@ static void strang2d_fused(Splitting2D &h, double dt, int64_t steps)
         if (s == 0) {
             hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);
             m2d_b_from_e(m, b, 0.5 * dt, e);
-            fused_he_hp3(h, dt, 1);
+            fused_he_hp3(h, dt, pending ? 2 : 1, pending ? h.pending_dt : dt);
         } else {
             GP_CUDA(cudaMemcpyAsync(h.eT(0), h.e(0), 3 * h.nd * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
             m2d_b_from_e(m, b, 0.5 * dt, e);              // trailing HE of step s-1, field part
             hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);     // trailing HB of step s-1
             hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);     // leading HB of step s
             m2d_b_from_e(m, b, 0.5 * dt, e);              // leading HE of step s, field part
-            fused_he_hp3(h, dt, 2);
+            fused_he_hp3(h, dt, 2, dt);
         }
         hs2d_operator(h, GEMPIC_OP_HP2, 0.5 * dt);
         hs2d_operator(h, GEMPIC_OP_HP1, dt);
@@ -1068,8 +1081,21 @@ static void strang2d_fused(Splitting2D &h, double dt, int64_t steps)
         hs2d_operator(h, GEMPIC_OP_HP3, 0.5 * dt);
         h.steps_done++;
     }
-    hs2d_operator(h, GEMPIC_OP_HE, 0.5 * dt);
+    // trailing HE + HB: the fields are advanced now; the particle kick, which only reads the snapshot eT, is deferred to
+    // the next call of this splitting or applied by pg_sync() as soon as anybody else touches the particles
+    GP_CUDA(cudaMemcpyAsync(h.eT(0), h.e(0), 3 * h.nd * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
+    m2d_b_from_e(m, b, 0.5 * dt, e);
     hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);
+    h.pending_dt = dt;
+    pg.pending2d = &h;
+}
+
+void hs2d_apply_pending(ParticleGroup &pg)
+{
+    Splitting2D *h = pg.pending2d;
+    if (!h) return;
+    pg.pending2d = nullptr;
+    op2_HE_particles(*h, 0.5 * h->pending_dt, h->eT(0), h->eT(1), h->eT(2));
 }
 
 void hs2d_strang(Splitting2D &h, double dt, int64_t steps)
@@ -1079,6 +1105,7 @@ void hs2d_strang(Splitting2D &h, double dt, int64_t steps)
         strang2d_fused(h, dt, steps);
         return;
     }
+    pg_sync(*h.pg);
     for (int64_t s = 0; s < steps; ++s) {
         if (h.sort_interval > 0 && h.steps_done % h.sort_interval == 0) pg_sort_2d(*h.pg, *h.maxwell);
         hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);
@@ -1128,6 +1155,7 @@ int gempic_hs2d_create(gempic_handle maxwell2d, gempic_handle pgh, gempic_handle
     GP_REQUIRE(h->maxwell->nx >= 2 * kR2 + 2 && h->maxwell->ny >= 2 * kR2 + 2, GEMPIC_EINVAL,
                "HamiltonianSplitting{2,3} needs at least %d cells per direction", 2 * kR2 + 2);
     h->nd = (size_t)h->maxwell->nx * h->maxwell->ny;
+    h->pg_handle = pgh;
     h->fields.alloc(13 * h->nd + 16);
     h->fields.zero(ctx().stream);
     *out = register_object(std::move(h));
@@ -1137,6 +1165,12 @@ int gempic_hs2d_create(gempic_handle maxwell2d, gempic_handle pgh, gempic_handle
 int gempic_hs2d_destroy(gempic_handle hs)
 {
     GP_API_BEGIN
+    Splitting2D *h = get<Splitting2D>(hs, "HamiltonianSplitting{2,3}");
+    try {   // a deferred HE kick must not be lost; the particle group may already be gone
+        ParticleGroup *pg = get<ParticleGroup>(h->pg_handle, "ParticleGroup");
+        if (pg->pending2d == h) pg_sync(*pg);
+    } catch (const Fail &) {
+    }
     destroy(hs, Kind::Splitting2D, "HamiltonianSplitting{2,3}");
     GP_API_END
 }
@@ -1175,7 +1209,9 @@ int gempic_hs2d_operator(gempic_handle hs, int op, double dt)
 {
     GP_API_BEGIN
     require_init();
-    hs2d_operator(*get<Splitting2D>(hs, "HamiltonianSplitting{2,3}"), op, dt);
+    Splitting2D *h = get<Splitting2D>(hs, "HamiltonianSplitting{2,3}");
+    pg_sync(*h->pg);
+    hs2d_operator(*h, op, dt);
     GP_API_END
 }
 
@@ -1234,6 +1270,7 @@ int gempic_hs2d_charge_density(gempic_handle hs, double *rho)
     require_init();
     Splitting2D *h = get<Splitting2D>(hs, "HamiltonianSplitting{2,3}");
     GP_REQUIRE(rho, GEMPIC_EINVAL, "null buffer");
+    pg_sync(*h->pg);
     double *dr = h->fields.p + 9 * h->nd;
     hs2d_charge(*h, dr);
     d2h(rho, dr, h->nd);
@@ -1247,6 +1284,7 @@ int gempic_hs2d_moments(gempic_handle hs, double *out4)
     require_init();
     Splitting2D *h = get<Splitting2D>(hs, "HamiltonianSplitting{2,3}");
     GP_REQUIRE(out4, GEMPIC_EINVAL, "null buffer");
+    pg_sync(*h->pg);
     double *d = h->fields.p + 13 * h->nd;
     hs2d_moments(*h, d);
     d2h(out4, d, 4);

@@ -8,12 +8,14 @@ namespace gempic {
 // ParticleGroup{D,V} (src/particle_group.jl:15-46): device SoA, one fp64 row per
 // coordinate, rows ordered x1..xD, v1..vV, w1..wW like the rows of the reference array.
 struct Splitting;
+struct Splitting2D;
 struct ParticleGroup : Object {
     static constexpr Kind kKind = Kind::ParticleGroup;
     // A fused strang_splitting! call may leave its trailing operatorHE kick pending (hs1d.cu): the velocities lag
     // by that kick until the owner's next call folds it into its first pass, or pg_sync() applies it because
     // somebody else is about to look at the particles.
     Splitting *pending = nullptr;
+    Splitting2D *pending2d = nullptr;   // the same for HamiltonianSplitting{2,3} (hs2d.cu)
     int D, V, W;
     int64_t n;
     double charge, mass, common_weight, q_over_m;
@@ -198,6 +200,8 @@ struct Splitting2D : Object {
     PartialScratch scratch;
     int sort_interval = 1;     // cell-sort every k Strang steps (0: never)
     int64_t steps_done = 0;
+    double pending_dt = 0.0;   // dt of the deferred trailing HE kick (ParticleGroup::pending2d == this; fields in eT)
+    gempic_handle pg_handle = 0;
     Splitting2D() : Object(kKind) {}
     double *e(int c) { return fields.p + (size_t)c * nd; }
     double *b(int c) { return fields.p + (size_t)(3 + c) * nd; }
@@ -205,6 +209,7 @@ struct Splitting2D : Object {
     double *eT(int c) { return fields.p + (size_t)(10 + c) * nd; }
 };
 void hs2d_operator(Splitting2D &h, int op, double dt);
+void hs2d_apply_pending(ParticleGroup &pg);   // the deferred trailing HE kick of a fused 2d3v strang_splitting (hs2d.cu)
 void hs2d_strang(Splitting2D &h, double dt, int64_t steps);
 void pg_sort_2d(ParticleGroup &pg, const Maxwell2D &m);
 void sort_scan(int *counts, int64_t total);   // exclusive prefix sum in place (particles.cu)

@@ -143,6 +143,27 @@ def test_strang_fused_and_unfused_match_oracle(gp, fuse):
     check(ho, hg, BOX, tol=1e-10, what=f"strang fuse={fuse}")
 
 
+def test_deferred_trailing_kick_is_invisible(gp):
+    """the fused 2d3v strang_splitting! defers its trailing HE particle kick to its next call (hs2d.cu, pending2d): no
+    sequence of calls may observe the lag -- varying dt, particle downloads, single operators and moments in between"""
+    ho, hg = build(gp, 8_000, 16, 12, 3, seed=77, resident=False)
+    for dt in (0.05, 0.03, 0.07):                      # back to back: the kick rides in the next call's first pass
+        ho.strang_splitting(dt, 1), hg.strang_splitting(dt, 1)
+        for c in range(3):
+            assert rel(hg.e_dofs[c], ho.e_dofs[c]) < 1e-10 and rel(hg.b_dofs[c], ho.b_dofs[c]) < 1e-10
+    check(ho, hg, BOX, tol=1e-10, what="download after three calls")      # the download applies the pending kick
+    ho.strang_splitting(0.05, 2), hg.strang_splitting(0.05, 2)
+    ho.operatorHp1(0.02), hg.operatorHp1(0.02)         # a single operator after a fused call
+    check(ho, hg, BOX, tol=1e-10, what="operator after strang")
+    ho.strang_splitting(0.04, 1), hg.strang_splitting(0.04, 1)
+    a = ho.particle_group.array
+    ke_ref = float(np.sum(a[5] * (a[2] ** 2 + a[3] ** 2 + a[4] ** 2)))
+    m = hg.moments()                                   # sum_p w |v|^2 must see the kick
+    assert abs(m[0] - ke_ref) < 1e-10 * ke_ref
+    ho.strang_splitting(0.05, 1), hg.strang_splitting(0.05, 1)
+    check(ho, hg, BOX, tol=1e-9, what="after moments")
+
+
 def test_invariants_at_scale(gp):
     """2e6 particles on 64x64, degree 3 (the BASELINE config 5 grid): Gauss law conserved to round-off,
     total charge exact, energy drift O(dt^2)"""
