@@ -206,22 +206,25 @@ struct OpHp1 {
 // 87-96 % of peak), so it is laid out to touch as few shared-memory words per particle as possible:
 //   * the fields are staged in pp form (the reference's b_to_pp / evaluate_pp, splinepp.jl:241-285,
 //     pmc1d.jl:242-250): per cell the D+1 polynomial coefficients of  E1 = sum_h dt_h q/m e1^(h),
-//     E2 likewise, and of the PRIMITIVE of b.  One set of D1+1 coefficients of b then serves the
-//     Hp2 gather at the old position, the line integral  int b dx  of Hp1 (Q(t_new) - Q(t_old), plus
-//     whole-cell terms for the few particles that cross a boundary) and the Hp2 gather at the new
-//     position: 3 loads instead of 10, and the kicks of all NHE electric fields cost one Horner each;
+//     E2 likewise, and of the cell-cumulative ANTIDERIVATIVE G of b.  One set of D1+1 coefficients of b
+//     then serves the Hp2 gather at the old position, the line integral  int b dx = G(new) - G(old)  of
+//     Hp1 and the Hp2 gather at the new position: 3 loads instead of 10 (the lanes whose particle
+//     changes cell load the new cell's set and the two cell constants with predicated LDS), and the
+//     kicks of all NHE electric fields cost one Horner each;
 //   * every staged coefficient exists in 16 lane-interleaved copies (Op::FIELD_COPIES): a gather is
 //     conflict free for any cell pattern;
 //   * deposits are read-modify-writes of lane-private grids (pass.cuh), one contiguous window
 //     per grid and particle, issued after the branch-free arithmetic of a whole quad:
-//       j2           D0+1 slots at the old cell, then D0+1 slots at the wrapped new position.  Both
-//                    Hp2 half steps add into ONE grid: the two compute_e_from_j!(e2, ., 2) solves are
+//       j2           D0+1 slots at the old cell, holding BOTH Hp2 deposits when the particle stays in
+//                    its cell; only the lanes that changed cell touch a second window at the new one.
+//                    Both half steps add into ONE grid: the two compute_e_from_j!(e2, ., 2) solves are
 //                    linear and nothing reads e2 in between, so e2 -= M0^-1 (dt/2)(j2a + j2b)/dx.
 //                    (j_dofs[2] as the reference leaves it -- dt/2 * j2b -- is rebuilt on demand from
 //                    the particles, hs1d.cu materialise_j2.)
 //       j1           D1+2 slots starting at min(cell_old, cell_new): the old-cell and new-cell
-//                    segments of add_current_update_v! merged;
-//   * one block of 8 warps per SM: 8 x 2 lane-private grids + the coefficient copies = 187 KB.
+//                    segments of add_current_update_v! merged (the last one predicated: it is zero
+//                    unless the cell changed);
+//   * one block of 8 warps per SM: 8 x 2 lane-private grids + the coefficient copies = 191 KB.
 // Particles that move more than one cell (or sit outside one period) take the general
 // per-particle code (apply) instead, which reads the dof-form fields from global memory.
 template <int D0, int D1>
