@@ -164,6 +164,43 @@ def test_deferred_trailing_kick_is_invisible(gp):
     check(ho, hg, BOX, tol=1e-9, what="after moments")
 
 
+def test_strang_round_trip_at_scale(gp):
+    """size-independent property: every sub-flow is exact and the Strang composition symmetric, so three steps forward
+    and three steps back (dt -> -dt) return 3e5 particles and all six fields to their start to round-off -- with the
+    sort riding in the pushes (particles are matched through their distinct weights) and the deferred trailing kick"""
+    n, nx = 300_000, 32
+    box = ((0.0, 4 * np.pi), (0.0, 4 * np.pi))
+    st = make_state(n, box, seed=91)
+    st[5] = (4 * np.pi) ** 2 * (1.0 + np.random.default_rng(92).permutation(n) / n)   # distinct weights = particle ids
+    nd = nx * nx
+    ix, iy = np.arange(nd) % nx, np.arange(nd) // nx
+    mode = lambda a, b, ph: 0.05 * np.cos(2 * np.pi * (a * ix + b * iy) / nx + ph)
+    e0 = [mode(1, 0, 0.3), mode(0, 1, 1.1), mode(1, 1, 2.0)]
+    b0 = [mode(1, 1, 0.7), mode(1, 0, 1.9), mode(0, 1, 0.2)]
+    pg = gp.ParticleGroup(2, 3, n, charge=-1.0)
+    pg.upload(st)
+    mg = gp.TwoDMaxwell(gp.TwoDGrid(0.0, 4 * np.pi, nx, 0.0, 4 * np.pi, nx), 3)
+    e, b = [v.copy() for v in e0], [v.copy() for v in b0]
+    h = gp.HamiltonianSplitting2D3V(mg, pg, e, b, resident=True)
+    h.strang_splitting(0.05, 2)
+    h.strang_splitting(0.05, 1)
+    mid = pg.to_host()
+    assert np.max(np.abs(np.sort(mid[2]) - np.sort(st[2]))) > 1e-4            # something happened
+    h.strang_splitting(-0.05, 1)
+    h.strang_splitting(-0.05, 2)
+    h.sync_fields()
+    a = pg.to_host()
+    ka, kb = np.argsort(a[5]), np.argsort(st[5])
+    a, ref = a[:, ka], st[:, kb]
+    assert np.array_equal(a[5], ref[5])
+    for d in range(2):
+        dx = np.abs(a[d] - ref[d])
+        assert np.max(np.minimum(dx, np.abs(dx - 4 * np.pi))) < 1e-11
+    assert np.max(np.abs(a[2:5] - ref[2:5])) < 1e-11
+    for c in range(3):
+        assert np.max(np.abs(e[c] - e0[c])) < 1e-11 and np.max(np.abs(b[c] - b0[c])) < 1e-11
+
+
 def test_invariants_at_scale(gp):
     """2e6 particles on 64x64, degree 3 (the BASELINE config 5 grid): Gauss law conserved to round-off,
     total charge exact, energy drift O(dt^2)"""

@@ -154,3 +154,48 @@ def test_gauss_law_is_conserved_over_strang_steps():
     # positions stay inside the periodic box
     assert np.all((pg.array[0] >= -1.0) & (pg.array[0] < -1.0 + L1))
     assert np.all((pg.array[1] >= 0.5) & (pg.array[1] < 3.5))
+
+
+def _fresh(n, seed, amp=0.05):
+    _, pg, mx = make_2d(n, seed=seed)
+    rng = np.random.default_rng(seed + 100)
+    pg.array[4] = 0.3 * rng.normal(size=n)
+    nd = NX * NY
+    # smooth fields (a few low modes) so that the O(dt^2) regime is reached at dt ~ 0.1
+    ix, iy = np.arange(nd) % NX, np.arange(nd) // NX
+    mode = lambda a, b, ph: np.cos(2 * np.pi * (a * ix / NX + b * iy / NY) + ph)
+    e = [amp * mode(1, 0, 0.3), amp * mode(0, 1, 1.1), amp * mode(1, 1, 2.0)]
+    b = [amp * mode(1, 1, 0.7), amp * mode(1, 0, 1.9), amp * mode(0, 1, 0.2)]
+    return s2.HamiltonianSplitting2D3V(mx, pg, e, b)
+
+
+def test_strang_step_is_time_reversible():
+    """(d) every sub-flow is solved exactly and the Strang composition is symmetric, so S(-dt) S(dt) = id to round-off:
+    particles, all six field components and the currents' effect come back"""
+    h = _fresh(2000, seed=41)
+    x0 = h.particle_group.array.copy()
+    e0, b0 = [v.copy() for v in h.e_dofs], [v.copy() for v in h.b_dofs]
+    h.strang_splitting(0.05, 3)
+    assert np.max(np.abs(h.particle_group.array[2:5] - x0[2:5])) > 1e-4      # something happened
+    h.strang_splitting(-0.05, 3)
+    a = h.particle_group.array
+    for d, L in ((0, L1), (1, 3.0)):
+        dx = np.abs(a[d] - x0[d])
+        assert np.max(np.minimum(dx, np.abs(dx - L))) < 1e-12
+    assert np.max(np.abs(a[2:5] - x0[2:5])) < 1e-12
+    for c in range(3):
+        assert np.max(np.abs(h.e_dofs[c] - e0[c])) < 1e-12 and np.max(np.abs(h.b_dofs[c] - b0[c])) < 1e-12
+
+
+def test_strang_splitting_is_second_order():
+    """(e) global error against a dt/16 solution of the same semi-discrete system falls by ~4 when dt is halved"""
+    T = 0.4
+
+    def run(dt):
+        h = _fresh(1500, seed=43)
+        h.strang_splitting(dt, int(round(T / dt)))
+        return np.concatenate([h.particle_group.array[2:5].ravel()] + [v for v in h.e_dofs] + [v for v in h.b_dofs])
+
+    ref = run(T / 64)
+    err = [np.max(np.abs(run(dt) - ref)) for dt in (T / 4, T / 8)]
+    assert 3.0 < err[0] / err[1] < 5.5, err
