@@ -110,14 +110,22 @@ __global__ void k_strang_fields(StrangFields F)
     double *e1 = sh + n, *e2 = e1 + n, *b = e2 + n, *acc = b + n, *eT = acc + 2 * n;
     double *c0 = eT + 2 * n, *c1 = c0 + n, *ca = c1 + n;
     if (F.n_partials >= 0) {
-        // acc[g] = sum_b partials[b][g]: one warp per output, the summation order of k_reduce_partials
-        const int lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-        for (int o = threadIdx.x >> 5; o < F.n_acc; o += nw) {
-            double s = 0.0;
-            for (int k = lane; k < F.n_partials; k += 32) s += F.partials[(size_t)k * F.n_acc + o];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
-            if (lane == 0) acc[o] = s;
+        // acc[g] = sum_b partials[b][g].  Thread t owns output t % n_acc and every (blockDim / n_acc)-th block row, so
+        // all its loads are independent and in flight together (coalesced along g); the few row-group sums of an
+        // output are then added in a fixed order.  (n_acc = 2n <= 256 threads; red = 4 * n_acc doubles after the tables)
+        double *red = ca + n;
+        const int groups = blockDim.x / F.n_acc;
+        const int o = threadIdx.x % F.n_acc, grp = threadIdx.x / F.n_acc;
+        if (grp < groups) {
+            double sum = 0.0;
+            for (int k = grp; k < F.n_partials; k += groups) sum += F.partials[(size_t)k * F.n_acc + o];
+            red[grp * F.n_acc + o] = sum;
+        }
+        __syncthreads();
+        for (int g = threadIdx.x; g < F.n_acc; g += blockDim.x) {
+            double sum = 0.0;
+            for (int q = 0; q < groups; ++q) sum += red[q * F.n_acc + g];
+            acc[g] = sum;
         }
     } else if (F.do_solve) {
         for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) acc[i] = F.acc[i];
@@ -277,8 +285,11 @@ void field_strang_fields(const Maxwell1D &m, StrangFields F)
     F.ampere = m.col(Maxwell1D::C_AMPERE);
     F.n = m.n;
     F.dx = m.delta_x;
-    const int threads = F.n_partials >= 0 ? 256 : field_threads(m.n);
-    k_strang_fields<<<1, threads, 12 * (size_t)m.n * sizeof(double), ctx().stream>>>(F);
+    // with partials to reduce: a multiple of n_acc = 2n threads (n <= 64 for the fused path), 4 row groups
+    const int threads = F.n_partials >= 0 ? 4 * F.n_acc : field_threads(m.n);
+    GP_REQUIRE(threads <= 1024, GEMPIC_EINVAL, "fused field kernel: grid of %d dofs is too large", m.n);
+    k_strang_fields<<<1, threads, (12 * (size_t)m.n + 4 * (size_t)(F.n_partials >= 0 ? F.n_acc : 0)) * sizeof(double),
+                      ctx().stream>>>(F);
     GP_CUDA(cudaGetLastError());
     count_launch();
 }
