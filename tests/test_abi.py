@@ -63,3 +63,124 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".jl")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in src.lower(), f"{f} references the oracle"
+
+
+def _c_prototypes():
+    """name -> number of parameters, from include/gempic_b200.h"""
+    text = open(os.path.join(ROOT, "include", "gempic_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
+    protos = {}
+    for m in re.finditer(r"\b(gempic_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        if name in ("gempic_func1d", "gempic_func2d"):
+            continue
+        protos[name] = 0 if params in ("", "void") else len(_split_top(params))
+    return protos
+
+
+def _split_top(s):
+    """split on commas that are not inside parentheses / brackets"""
+    parts, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        parts.append(cur)
+    return parts
+
+
+def _julia_ccalls():
+    """(symbol, number of argument types, number of arguments) of every ccall in julia/GEMPICB200.jl"""
+    text = open(os.path.join(ROOT, "julia", "GEMPICB200.jl")).read()
+    text = re.sub(r"#[^\n]*", "", text)
+    out = []
+    for m in re.finditer(r"ccall\(\(:(gempic_[a-z0-9_]+),\s*LIB\)\s*,", text):
+        i, depth = m.end(), 1            # scan to the parenthesis that closes ccall(
+        j = i
+        while depth:
+            depth += {"(": 1, ")": -1}.get(text[j], 0)
+            j += 1
+        args = _split_top(text[i:j - 1])    # return type, (argument types...), arguments...
+        types = args[1].strip()
+        assert types.startswith("(") and types.endswith(")"), (m.group(1), types)
+        inner = types[1:-1].strip().rstrip(",")
+        n_types = 0 if not inner else len(_split_top(inner))
+        out.append((m.group(1), n_types, len(args) - 2))
+    return out
+
+
+def test_julia_shim_binds_the_declared_prototypes():
+    """Julia is not installed here, so the shim is checked statically: every ccall names an entry point declared in the
+    header, with as many argument types -- and as many arguments -- as the C prototype has parameters."""
+    protos = _c_prototypes()
+    calls = _julia_ccalls()
+    assert len(calls) >= 40
+    for name, n_types, n_args in calls:
+        assert name in protos, f"{name} is not declared in include/gempic_b200.h"
+        assert n_types == protos[name], f"{name}: {n_types} ccall argument types, {protos[name]} C parameters"
+        assert n_args == n_types, f"{name}: {n_args} arguments for {n_types} argument types"
+
+
+def _c_param_class(p):
+    p = re.sub(r"\bconst\b", "", p).strip()
+    stars = p.count("*")
+    base = re.sub(r"[\*\s]+[A-Za-z_0-9\[\]]*$", "", p.replace("*", " * ")).strip() if stars else p.rsplit(None, 1)[0].strip()
+    base = re.sub(r"\s+", " ", base.replace("*", "")).strip()
+    if base in ("gempic_func1d", "gempic_func2d"):
+        return "ptr"
+    if base == "gempic_handle":
+        return "handle*" if stars else "handle"
+    if base == "double":
+        return "double*" if stars else "double"
+    if base == "int":
+        return "int*" if stars else "int"
+    if base == "int64_t":
+        return "int64*" if stars else "int64"
+    if base == "uint64_t":
+        return "uint64*" if stars else "uint64"
+    if base in ("void", "char"):
+        return "ptr"
+    return base + ("*" * stars)
+
+
+_JL = {"Handle": "handle", "UInt64": "handle", "Cint": "int", "Int64": "int64", "Cdouble": "double", "Cstring": "ptr",
+       "Ref{Handle}": "handle*", "Ptr{Handle}": "handle*", "Ptr{Cdouble}": "double*", "Ref{Cdouble}": "double*",
+       "Ptr{Cvoid}": "ptr", "Ptr{UInt8}": "ptr", "Ref{Cint}": "int*", "Ptr{Cint}": "int*", "Ref{Int64}": "int64*",
+       "Ptr{Int64}": "int64*", "Ptr{Ptr{Cdouble}}": "double*", "Ref{Ptr{Cdouble}}": "double*"}
+
+
+def test_julia_shim_argument_types_match_the_header():
+    """same static check, type by type (handle, int, int64, double and their pointers)"""
+    htext = open(os.path.join(ROOT, "include", "gempic_b200.h")).read()
+    htext = re.sub(r"/\*.*?\*/", "", htext, flags=re.S)
+    cparams = {}
+    for m in re.finditer(r"\b(gempic_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", htext, flags=re.S):
+        ps = m.group(2).strip()
+        cparams[m.group(1)] = [] if ps in ("", "void") else [_c_param_class(p) for p in _split_top(ps)]
+    jtext = re.sub(r"#[^\n]*", "", open(os.path.join(ROOT, "julia", "GEMPICB200.jl")).read())
+    checked = 0
+    for m in re.finditer(r"ccall\(\(:(gempic_[a-z0-9_]+),\s*LIB\)\s*,", jtext):
+        i, depth = m.end(), 1
+        j = i
+        while depth:
+            depth += {"(": 1, ")": -1}.get(jtext[j], 0)
+            j += 1
+        types = _split_top(jtext[i:j - 1])[1].strip()[1:-1].strip().rstrip(",")
+        jl = [t.strip() for t in _split_top(types)] if types else []
+        want = cparams[m.group(1)]
+        for k, (jt, ct) in enumerate(zip(jl, want)):
+            assert jt in _JL, f"{m.group(1)} argument {k}: unknown Julia type {jt}"
+            got = _JL[jt]
+            ok = (got == ct or (ct == "uint64" and got == "handle") or (ct == "uint64*" and got == "handle*")
+                  or (ct == "double**" and got == "double*"))
+            assert ok, f"{m.group(1)} argument {k}: Julia {jt} vs C {ct}"
+            checked += 1
+    assert checked > 150
