@@ -1,0 +1,49 @@
+"""The CPU arm of bench.py (`--impl reference`) runs without a GPU: check the one-JSON-line contract on it."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_reference(*extra):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--cpu-particles", "40000", *extra], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, "stdout must carry exactly one JSON line"
+    return json.loads(lines[0])
+
+
+def check_line(d):
+    assert d["impl"] == "reference"
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["unit"] == "particle-steps/s" and d["higher_is_better"] is True and d["dtype"] == "f64"
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["scaling"] == "weak"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    e = d["e2e"]
+    assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+
+
+def test_reference_arm_1d2v():
+    check_line(run_reference())
+
+
+def test_reference_arm_other_workloads():
+    for wl in ("boris", "2d3v"):
+        d = run_reference("--workload", wl)
+        check_line(d)
+        assert wl.lower() in d["config"]["workload"].lower() or wl == "boris"
+
+
+def test_reference_arm_under_torchrun_env_prints_on_rank0_only():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1", MASTER_ADDR="127.0.0.1", MASTER_PORT="29555")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
