@@ -71,9 +71,11 @@ void boris_staggering(Boris &s, double dt)   // :99-122
     boris_fields_after_push(s, 0.5 * dt, 0.5 * dt);
 }
 
-static void boris_fields(Boris &s, bool post, bool pre, double dt)
+static void boris_fields(Boris &s, bool post, bool pre, double dt, const DeferredReduce *defer = nullptr)
 {
     BorisFields F{};
+    F.n_partials = defer ? defer->n_blocks : -1;
+    F.partials = defer ? defer->partials : nullptr;
     F.e1 = s.f(GEMPIC_F_E1); F.e2 = s.f(GEMPIC_F_E2); F.b = s.f(GEMPIC_F_B);
     F.j1 = s.f(GEMPIC_F_J1); F.j2 = s.f(GEMPIC_F_J2);
     F.e1_mid = s.f(GEMPIC_F_E1_MID); F.e2_mid = s.f(GEMPIC_F_E2_MID); F.b_mid = s.f(GEMPIC_F_B_MID);
@@ -84,7 +86,7 @@ static void boris_fields(Boris &s, bool post, bool pre, double dt)
 
 // (2)+(3) of a step: the fused particle pass while its lane-private grids and pp tables fit in shared memory
 // (n <~ 40 cells at degree 3), else the four reference loops one by one
-static void boris_particles(Boris &s, double dt)
+static void boris_particles(Boris &s, double dt, DeferredReduce *defer)
 {
     bool fused = false;
     GP_DISPATCH_DEGREES(s.ks0->degree, s.ks1->degree, {
@@ -99,12 +101,13 @@ static void boris_particles(Boris &s, double dt)
             P.fields[2] = s.f(GEMPIC_F_B_MID);
             const double cq = s.pg->charge * s.pg->common_weight;
             P.op = {dt, (0.5 * dt) * s.pg->q_over_m, s.pg->q_over_m * 0.5 * dt, cq * s.ks0->scaling, cq * s.ks1->scaling};
-            launch_pass<Op>(P, &s.scratch, s.f(GEMPIC_F_J1), "boris_step");
+            launch_pass<Op>(P, &s.scratch, s.f(GEMPIC_F_J1), "boris_step", defer);
         }
     });
     if (fused) {
-        allreduce_sum(s.f(GEMPIC_F_J1), 2 * s.n);
+        if (!defer) allreduce_sum(s.f(GEMPIC_F_J1), 2 * s.n);
     } else {
+        if (defer) defer->n_blocks = -1;   // the separate passes reduce (and all-reduce) j1, j2 themselves
         boris_push_v_epart(s, 0.5 * dt);
         boris_push_v_bpart(s, dt);
         boris_push_v_epart(s, 0.5 * dt);
@@ -118,9 +121,12 @@ void boris_strang(Boris &s, double dt, int64_t steps)
 {
     if (steps <= 0) return;
     boris_fields(s, false, true, dt);
+    // one GPU: the per-block partial sums of the pass are reduced by the field kernel itself (one launch less)
+    const bool single = ctx().n_ranks == 1;
     for (int64_t i = 0; i < steps; ++i) {
-        boris_particles(s, dt);
-        boris_fields(s, true, i + 1 < steps, dt);
+        DeferredReduce dr, *defer = single ? &dr : nullptr;
+        boris_particles(s, dt, defer);
+        boris_fields(s, true, i + 1 < steps, dt, defer && defer->n_blocks >= 0 ? defer : nullptr);
     }
 }
 

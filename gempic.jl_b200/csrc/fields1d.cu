@@ -248,6 +248,25 @@ __global__ void k_boris_fields(BorisFields F)
 {
     extern __shared__ double sh[];
     const int n = F.n;
+    if (F.n_partials >= 0) {
+        // j1 | j2 (adjacent) = sum over the block rows of the pass, like k_strang_fields: thread t owns output t % 2n and
+        // every 4th row, then the four row-group sums are added in a fixed order
+        double *red = sh + n;
+        const int n_acc = 2 * n, groups = blockDim.x / n_acc;
+        const int o = threadIdx.x % n_acc, grp = threadIdx.x / n_acc;
+        if (grp < groups) {
+            double sum = 0.0;
+            for (int k = grp; k < F.n_partials; k += groups) sum += F.partials[(size_t)k * n_acc + o];
+            red[grp * n_acc + o] = sum;
+        }
+        __syncthreads();
+        for (int g = threadIdx.x; g < n_acc; g += blockDim.x) {
+            double sum = 0.0;
+            for (int q = 0; q < groups; ++q) sum += red[q * n_acc + g];
+            F.j1[g] = sum;   // j1 | j2 are adjacent
+        }
+        __syncthreads();
+    }
     if (F.do_post) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             F.e1[i] = F.e1_mid[i];
@@ -273,7 +292,10 @@ void field_boris_fields(const Maxwell1D &m, BorisFields F)
     F.ampere = m.col(Maxwell1D::C_AMPERE);
     F.n = m.n;
     F.dx = m.delta_x;
-    k_boris_fields<<<1, field_threads(m.n), m.n * sizeof(double), ctx().stream>>>(F);
+    const bool red = F.n_partials >= 0;
+    const int threads = red ? 8 * m.n : field_threads(m.n);
+    GP_REQUIRE(threads <= 1024, GEMPIC_EINVAL, "fused field kernel: grid of %d dofs is too large", m.n);
+    k_boris_fields<<<1, threads, (red ? 9 : 1) * (size_t)m.n * sizeof(double), ctx().stream>>>(F);
     GP_CUDA(cudaGetLastError());
     count_launch();
 }

@@ -106,6 +106,9 @@ struct BorisFields {
     double dx;
     int do_post, do_pre;
     double dt_post, dt_pre;
+    // single GPU: per-block partial sums [j1 | j2] of the pass, reduced into j1, j2 by this kernel (n_partials < 0: done)
+    const double *partials;
+    int n_partials;
 };
 void field_boris_fields(const Maxwell1D &m, BorisFields F);
 void field_b_from_e(const Maxwell1D &m, double *b, double dt, const double *e);
