@@ -16,7 +16,8 @@ export OneDGrid, TwoDGrid, ParticleGroup, ParticleMeshCoupling1D, Maxwell1DFEM, 
        operatorHp1, operatorHp2, operatorHE, operatorHB, solve_poisson!,
        add_charge!, evaluate, add_current_update_v!, compute_e_from_rho!, compute_e_from_j!,
        compute_e_from_b!, compute_b_from_e!, inner_product, l2norm_squared, l2projection!,
-       compute_rhs_from_function!, write_step!, upload!, download!, save, load!
+       compute_rhs_from_function!, write_step!, upload!, download!, save, load!,
+       get_x, get_v, get_charge, get_mass, set_x!, set_v!, set_weights!
 
 import FileIO            # save / load! write the reference's JLD2 particle dump (GEMPIC.jl depends on FileIO + JLD2)
 using Printf: @sprintf
@@ -52,14 +53,18 @@ struct OneDGrid
 end
 
 # ---- ParticleGroup{D,V} (src/particle_group.jl:15-46) -------------------------------------------
-# `array` keeps the reference layout (D+V+W) x N.  It is the *host mirror*: `upload!` after filling
-# it (sampling), `download!` before reading it.  `getproperty(pg, :array)` could do this lazily with
-# a dirty flag (as the Python mirror does); kept explicit here so that a 1e9-particle run never
-# copies 32 GB by accident.
+# The particles live on the device.  `pg.array` is a lazily synchronised host mirror in the reference layout
+# (D+V+W) x N (SURVEY section 8b): reading the property downloads the rows if the device has advanced since the last
+# download, and -- because the caller may write into the returned array, as the reference's samplers and set_x/set_v/
+# set_weights do -- marks the mirror as newer, so the next device operation uploads it first.  A 1e9-particle run that
+# never touches `pg.array` never copies anything (host_mirror = false does not even allocate it); `upload!` /
+# `download!` remain for explicit control.
 mutable struct ParticleGroup{D,V}
     dims::Tuple{Int,Int}
     n_particles::Int
-    array::Array{Float64,2}
+    host::Array{Float64,2}
+    host_newer::Bool
+    dev_newer::Bool
     common_weight::Float64
     charge::Float64
     mass::Float64
@@ -74,20 +79,52 @@ mutable struct ParticleGroup{D,V}
         check(ccall((:gempic_pg_create, LIB), Cint,
                     (Cint, Cint, Cint, Int64, Cdouble, Cdouble, Cdouble, Ref{Handle}),
                     D, V, n_weights, n_particles, charge, mass, common_weight, h))
-        array = host_mirror ? zeros(Float64, D + V + n_weights, n_particles) : zeros(Float64, D + V + n_weights, 0)
-        pg = new(( D, V ), n_particles, array, common_weight, charge, mass, n_weights, charge / mass, h[])
+        host = host_mirror ? zeros(Float64, D + V + n_weights, n_particles) : zeros(Float64, D + V + n_weights, 0)
+        pg = new(( D, V ), n_particles, host, false, false, common_weight, charge, mass, n_weights, charge / mass, h[])
         finalizer(p -> ccall((:gempic_pg_destroy, LIB), Cint, (Handle,), p.handle), pg)
         return pg
     end
 end
-upload!(pg::ParticleGroup) = check(ccall((:gempic_pg_upload, LIB), Cint, (Handle, Ptr{Cdouble}), pg.handle, pg.array))
-function download!(pg::ParticleGroup)
-    size(pg.array, 2) == pg.n_particles || (pg.array = zeros(Float64, sum(pg.dims) + pg.n_weights, pg.n_particles))
-    check(ccall((:gempic_pg_download, LIB), Cint, (Handle, Ptr{Cdouble}), pg.handle, pg.array))
-    return pg.array
+function upload!(pg::ParticleGroup)
+    host = getfield(pg, :host)
+    size(host, 2) == pg.n_particles || throw(ArgumentError("ParticleGroup: the host mirror holds $(size(host, 2)) of $(pg.n_particles) particles"))
+    check(ccall((:gempic_pg_upload, LIB), Cint, (Handle, Ptr{Cdouble}), pg.handle, host))
+    setfield!(pg, :host_newer, false)
+    setfield!(pg, :dev_newer, false)
+    return nothing
 end
+function download!(pg::ParticleGroup)
+    size(getfield(pg, :host), 2) == pg.n_particles ||
+        setfield!(pg, :host, zeros(Float64, sum(pg.dims) + pg.n_weights, pg.n_particles))
+    host = getfield(pg, :host)
+    check(ccall((:gempic_pg_download, LIB), Cint, (Handle, Ptr{Cdouble}), pg.handle, host))
+    setfield!(pg, :dev_newer, false)
+    return host
+end
+function Base.getproperty(pg::ParticleGroup, name::Symbol)
+    name === :array || return getfield(pg, name)
+    (getfield(pg, :dev_newer) || size(getfield(pg, :host), 2) != getfield(pg, :n_particles)) && download!(pg)
+    setfield!(pg, :host_newer, true)      # the caller may write into it
+    return getfield(pg, :host)
+end
+function Base.setproperty!(pg::ParticleGroup, name::Symbol, value)
+    name === :array || return setfield!(pg, name, convert(fieldtype(typeof(pg), name), value))
+    setfield!(pg, :host, convert(Array{Float64,2}, value))
+    setfield!(pg, :host_newer, true)
+    setfield!(pg, :dev_newer, false)
+    return value
+end
+# read-only view of the mirror (the reference's get_x / get_v / get_charge / get_mass): synchronised, not marked as written
+function _mirror(pg::ParticleGroup)
+    (getfield(pg, :dev_newer) || size(getfield(pg, :host), 2) != getfield(pg, :n_particles)) && download!(pg)
+    return getfield(pg, :host)
+end
+# before a device operation on the particles: push a host mirror the caller may have written; after one that changes them
+_flush(pg::ParticleGroup) = (getfield(pg, :host_newer) && upload!(pg); nothing)
+_touched(pg::ParticleGroup) = (setfield!(pg, :dev_newer, true); nothing)
 # save (src/particle_group.jl:152-165): the reference's JLD2 dump, from a fresh download of the device rows
 function save(file, step, p::ParticleGroup{D,V}) where {D,V}
+    _flush(p)
     a = download!(p)
     datafile = @sprintf("%s-%06d.jld2", file, step)
     FileIO.save(datafile, Dict("x" => a[1:D, :], "v" => a[(D + 1):(D + V), :], "w" => a[(D + V + 1):end, :]))
@@ -98,11 +135,22 @@ function load!(p::ParticleGroup{D,V}, datafile) where {D,V}
     p.array = vcat(d["x"], d["v"], d["w"])
     upload!(p)
 end
-get_x(p::ParticleGroup{D,V}, i::Int) where {D,V} = p.array[1:D, i]
-get_v(p::ParticleGroup{D,V}, i::Int) where {D,V} = p.array[(D + 1):(D + V), i]
-get_charge(p::ParticleGroup{D,V}, i::Int; i_wi = 1) where {D,V} = p.charge * p.array[D + V + i_wi, i] * p.common_weight
-get_mass(p::ParticleGroup{D,V}, i::Int; i_wi = 1) where {D,V} = p.mass * p.array[D + V + i_wi, i] * p.common_weight
-sort!(pg::ParticleGroup, pmc) = check(ccall((:gempic_pg_sort, LIB), Cint, (Handle, Handle), pg.handle, pmc.handle))
+get_x(p::ParticleGroup{D,V}, i::Int) where {D,V} = _mirror(p)[1:D, i]                    # src/particle_group.jl:53
+get_v(p::ParticleGroup{D,V}, i::Int) where {D,V} = _mirror(p)[(D + 1):(D + V), i]        # :60
+get_charge(p::ParticleGroup{D,V}, i::Int; i_wi = 1) where {D,V} = p.charge * _mirror(p)[D + V + i_wi, i] * p.common_weight   # :67-69
+get_mass(p::ParticleGroup{D,V}, i::Int; i_wi = 1) where {D,V} = p.mass * _mirror(p)[D + V + i_wi, i] * p.common_weight       # :76-78
+# set_x! / set_v! / set_weights! (:94-150): write the mirror; the next device operation uploads it
+set_x!(p::ParticleGroup{D,V}, i::Int, x::Vector{Float64}) where {D,V} = (p.array[1:D, i] .= x[1:D]; nothing)
+set_x!(p::ParticleGroup{D,V}, i::Int, x::Float64) where {D,V} = (p.array[1, i] = x; nothing)
+set_v!(p::ParticleGroup{D,V}, i::Int, v::Vector{Float64}) where {D,V} = (p.array[(D + 1):(D + V), i] .= v[1:V]; nothing)
+set_v!(p::ParticleGroup{D,V}, i::Int, v::Float64) where {D,V} = (p.array[D + 1, i] = v; nothing)
+set_weights!(p::ParticleGroup{D,V}, i::Int, w::Vector{Float64}) where {D,V} = (p.array[(D + V + 1):(D + V + p.n_weights), i] .= w; nothing)
+set_weights!(p::ParticleGroup{D,V}, i::Int, w::Float64) where {D,V} = (p.array[D + V + 1, i] = w; nothing)
+function sort!(pg::ParticleGroup, pmc)
+    _flush(pg)
+    check(ccall((:gempic_pg_sort, LIB), Cint, (Handle, Handle), pg.handle, pmc.handle))
+    _touched(pg)
+end
 
 # ---- ParticleMeshCoupling1D (src/particle_mesh_coupling_1d.jl:26-95) ----------------------------
 mutable struct ParticleMeshCoupling1D
@@ -238,18 +286,24 @@ function Base.getproperty(h::HamiltonianSplitting, name::Symbol)
     return j
 end
 const OP_HP1, OP_HP2, OP_HE, OP_HB = Cint(1), Cint(2), Cint(3), Cint(4)
-_op(h::HamiltonianSplitting, op::Cint, dt::Float64) =
+function _op(h::HamiltonianSplitting, op::Cint, dt::Float64)
+    _flush(h.particle_group)
     check(ccall((:gempic_hs_operator_host, LIB), Cint,
                 (Handle, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
                 h.handle, op, dt, h.e_dofs[1], h.e_dofs[2], h.b_dofs, C_NULL, C_NULL))
+    _touched(h.particle_group)
+end
 operatorHp1(h::HamiltonianSplitting, dt::Float64) = _op(h, OP_HP1, dt)   # src/hamiltonian_splitting_1d2v.jl:41-112 / _1d1v.jl:63-98
 operatorHp2(h::HamiltonianSplitting, dt::Float64) = _op(h, OP_HP2, dt)   # :129-176
 operatorHE(h::HamiltonianSplitting, dt::Float64) = _op(h, OP_HE, dt)     # :191-219
 operatorHB(h::HamiltonianSplitting, dt::Float64) = _op(h, OP_HB, dt)     # :234-236 / _1d1v.jl:113-125
-strang_splitting!(h::HamiltonianSplitting, dt::Float64, number_steps::Int) =   # src/hamiltonian_splitting.jl:98-108
+function strang_splitting!(h::HamiltonianSplitting, dt::Float64, number_steps::Int)   # src/hamiltonian_splitting.jl:98-108
+    _flush(h.particle_group)
     check(ccall((:gempic_hs_strang_splitting_host, LIB), Cint,
                 (Handle, Cdouble, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
                 h.handle, dt, number_steps, h.e_dofs[1], h.e_dofs[2], h.b_dofs, C_NULL, C_NULL))
+    _touched(h.particle_group)
+end
 
 # ---- HamiltonianSplittingBoris (src/hamiltonian_splitting_boris.jl:23-88) -----------------------
 struct HamiltonianSplittingBoris
@@ -267,12 +321,18 @@ struct HamiltonianSplittingBoris
         return new(maxwell_solver, kernel_smoother_0, kernel_smoother_1, particle_group, e_dofs, b_dofs, h[])
     end
 end
-staggering!(h::HamiltonianSplittingBoris, dt::Float64) =                     # :99-122
+function staggering!(h::HamiltonianSplittingBoris, dt::Float64)                     # :99-122
+    _flush(h.particle_group)
     check(ccall((:gempic_boris_staggering_host, LIB), Cint, (Handle, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
                 h.handle, dt, h.e_dofs[1], h.e_dofs[2], h.b_dofs))
-strang_splitting!(h::HamiltonianSplittingBoris, dt::Float64, number_steps::Int) =   # :132-177
+    _touched(h.particle_group)
+end
+function strang_splitting!(h::HamiltonianSplittingBoris, dt::Float64, number_steps::Int)   # :132-177
+    _flush(h.particle_group)
     check(ccall((:gempic_boris_strang_splitting_host, LIB), Cint, (Handle, Cdouble, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
                 h.handle, dt, number_steps, h.e_dofs[1], h.e_dofs[2], h.b_dofs))
+    _touched(h.particle_group)
+end
 
 # ---- TwoDGrid / TwoDMaxwell (src/mesh.jl:17-45, src/maxwell_2d_fem.jl:11-87) --------------------
 struct TwoDGrid
@@ -351,18 +411,25 @@ struct HamiltonianSplitting2D3V
     end
 end
 const OP_HP3 = Cint(5)
-_op(h::HamiltonianSplitting2D3V, op::Cint, dt::Float64) =
+function _op(h::HamiltonianSplitting2D3V, op::Cint, dt::Float64)
+    _flush(h.particle_group)
     check(ccall((:gempic_hs2d_operator_host, LIB), Cint, (Handle, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
                 h.handle, op, dt, h.e_dofs[1], h.e_dofs[2], h.e_dofs[3], h.b_dofs[1], h.b_dofs[2], h.b_dofs[3]))
+    _touched(h.particle_group)
+end
 operatorHp1(h::HamiltonianSplitting2D3V, dt::Float64) = _op(h, OP_HP1, dt)
 operatorHp2(h::HamiltonianSplitting2D3V, dt::Float64) = _op(h, OP_HP2, dt)
 operatorHp3(h::HamiltonianSplitting2D3V, dt::Float64) = _op(h, OP_HP3, dt)
 operatorHE(h::HamiltonianSplitting2D3V, dt::Float64) = _op(h, OP_HE, dt)
 operatorHB(h::HamiltonianSplitting2D3V, dt::Float64) = _op(h, OP_HB, dt)
-strang_splitting!(h::HamiltonianSplitting2D3V, dt::Float64, number_steps::Int) =
+function strang_splitting!(h::HamiltonianSplitting2D3V, dt::Float64, number_steps::Int)
+    _flush(h.particle_group)
     check(ccall((:gempic_hs2d_strang_splitting_host, LIB), Cint, (Handle, Cdouble, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
                 h.handle, dt, number_steps, h.e_dofs[1], h.e_dofs[2], h.e_dofs[3], h.b_dofs[1], h.b_dofs[2], h.b_dofs[3]))
+    _touched(h.particle_group)
+end
 function charge_density(h::HamiltonianSplitting2D3V)
+    _flush(h.particle_group)
     rho = zeros(h.maxwell_solver.mesh.nx * h.maxwell_solver.mesh.ny)
     check(ccall((:gempic_hs2d_charge_density, LIB), Cint, (Handle, Ptr{Cdouble}), h.handle, rho))
     return rho
@@ -371,6 +438,7 @@ end
 # ---- diagnostics (src/diagnostics.jl) --------------------------------------------------------------
 function solve_poisson!(efield::Vector{Float64}, particle_group::ParticleGroup, kernel_smoother_0::ParticleMeshCoupling1D,
                         maxwell_solver::Maxwell1DFEM, rho::Vector{Float64})            # :15-31
+    _flush(particle_group)
     check(ccall((:gempic_solve_poisson, LIB), Cint, (Handle, Handle, Handle, Ptr{Cdouble}, Ptr{Cdouble}),
                 particle_group.handle, kernel_smoother_0.handle, maxwell_solver.handle, efield, rho))
 end
@@ -378,6 +446,7 @@ end
 function write_step!(pg::ParticleGroup, maxwell::Maxwell1DFEM, ks0::ParticleMeshCoupling1D, ks1::ParticleMeshCoupling1D,
                      time, degree, efield_dofs, bfield_dofs, efield_dofs_n, efield_poisson)   # :186-250
     out = zeros(Float64, 11)
+    _flush(pg)
     check(ccall((:gempic_diag_write_step, LIB), Cint,
                 (Handle, Handle, Handle, Handle, Cdouble, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
                 pg.handle, maxwell.handle, ks0.handle, ks1.handle, time, degree, efield_dofs[1], efield_dofs[2], bfield_dofs,

@@ -184,3 +184,23 @@ def test_julia_shim_argument_types_match_the_header():
             assert ok, f"{m.group(1)} argument {k}: Julia {jt} vs C {ct}"
             checked += 1
     assert checked > 150
+
+
+def test_julia_shim_keeps_pg_array_coherent():
+    """`pg.array` is a lazily synchronised host mirror in the shim: every shim function that lets the device change the
+    particles flushes a written mirror first and marks it stale afterwards (static check: Julia is not installed here)"""
+    text = re.sub(r"#[^\n]*", "", open(os.path.join(ROOT, "julia", "GEMPICB200.jl")).read())
+    assert "function Base.getproperty(pg::ParticleGroup, name::Symbol)" in text
+    assert "function Base.setproperty!(pg::ParticleGroup, name::Symbol, value)" in text
+    movers = ("gempic_hs_operator_host", "gempic_hs_strang_splitting_host", "gempic_boris_staggering_host",
+              "gempic_boris_strang_splitting_host", "gempic_hs2d_operator_host", "gempic_hs2d_strang_splitting_host", "gempic_pg_sort")
+    readers = ("gempic_solve_poisson", "gempic_diag_write_step", "gempic_hs2d_charge_density")
+    # split into top-level function bodies ("function ... end" blocks at column 0)
+    blocks = re.findall(r"^function .*?^end", text, flags=re.S | re.M)
+    for sym in movers + readers:
+        body = [b for b in blocks if f":{sym}," in b]
+        assert body, f"{sym} is not called from a function block"
+        for b in body:
+            assert "_flush(" in b, f"{sym}: the written host mirror is not uploaded first"
+            if sym in movers:
+                assert "_touched(" in b, f"{sym}: the host mirror is not marked stale afterwards"
