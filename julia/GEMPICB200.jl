@@ -187,8 +187,10 @@ function add_charge!(rho_dofs::Vector{Float64}, p::ParticleMeshCoupling1D, posit
 end
 add_charge!(rho_dofs::Vector{Float64}, p::ParticleMeshCoupling1D, position::Float64, marker_charge::Float64) =
     add_charge!(rho_dofs, p, [position], [marker_charge])
-add_charge!(rho_dofs::Vector{Float64}, p::ParticleMeshCoupling1D, pg::ParticleGroup) =
+function add_charge!(rho_dofs::Vector{Float64}, p::ParticleMeshCoupling1D, pg::ParticleGroup)
+    _flush(pg)
     check(ccall((:gempic_pmc1d_add_charge_pg, LIB), Cint, (Handle, Handle, Ptr{Cdouble}), p.handle, pg.handle, rho_dofs))
+end
 function evaluate(p::ParticleMeshCoupling1D, position::Vector{Float64}, field_dofs::Vector{Float64})
     out = similar(position)
     check(ccall((:gempic_pmc1d_evaluate, LIB), Cint, (Handle, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Ptr{Cdouble}),

@@ -194,7 +194,7 @@ def test_julia_shim_keeps_pg_array_coherent():
     assert "function Base.setproperty!(pg::ParticleGroup, name::Symbol, value)" in text
     movers = ("gempic_hs_operator_host", "gempic_hs_strang_splitting_host", "gempic_boris_staggering_host",
               "gempic_boris_strang_splitting_host", "gempic_hs2d_operator_host", "gempic_hs2d_strang_splitting_host", "gempic_pg_sort")
-    readers = ("gempic_solve_poisson", "gempic_diag_write_step", "gempic_hs2d_charge_density")
+    readers = ("gempic_solve_poisson", "gempic_diag_write_step", "gempic_hs2d_charge_density", "gempic_pmc1d_add_charge_pg")
     # split into top-level function bodies ("function ... end" blocks at column 0)
     blocks = re.findall(r"^function .*?^end", text, flags=re.S | re.M)
     for sym in movers + readers:
