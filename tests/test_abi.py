@@ -204,3 +204,24 @@ def test_julia_shim_keeps_pg_array_coherent():
             assert "_flush(" in b, f"{sym}: the written host mirror is not uploaded first"
             if sym in movers:
                 assert "_touched(" in b, f"{sym}: the host mirror is not marked stale afterwards"
+
+
+def test_julia_shim_blocks_balance():
+    """coarse syntax check without Julia: block openers (function, struct, module, for, while, try, let, begin, if, do) and
+    `end`s balance once comments, strings and bracketed index expressions (`a[1:end]`) are stripped"""
+    text = open(os.path.join(ROOT, "julia", "GEMPICB200.jl")).read()
+    text = re.sub(r'"(?:\\.|[^"\\])*"', '""', text)
+    text = re.sub(r"#[^\n]*", "", text)
+    prev = None
+    while prev != text:
+        prev = text
+        text = re.sub(r"\[[^\[\]]*\]", "[]", text)
+    openers = closers = 0
+    for ln in text.splitlines():
+        for kw in ("function", "module", "for", "while", "try", "let", "begin", "quote", "macro"):
+            openers += len(re.findall(r"(?<![A-Za-z0-9_!.:])" + kw + r"(?![A-Za-z0-9_!])", ln))
+        openers += len(re.findall(r"(?<![A-Za-z0-9_!.])struct(?![A-Za-z0-9_!])", ln))
+        openers += len(re.findall(r"(?<![A-Za-z0-9_!])if\s", ln)) - len(re.findall(r"elseif\s", ln))
+        openers += 1 if re.search(r"\bdo(\s+[a-z_, ]+)?\s*$", ln.strip()) else 0
+        closers += len(re.findall(r"(?<![A-Za-z0-9_!:])end(?![A-Za-z0-9_!])", ln))
+    assert openers == closers and openers > 30, (openers, closers)
