@@ -13,6 +13,7 @@ from ._lib import ArgumentError, AssertionFailed, GempicError, finalize, init, l
 from .api import *  # noqa: F401,F403
 from .api import __all__ as _api_all
 from .dist import DistributedContext, shard_range  # noqa: F401
+from .selfcheck import sharded_parity  # noqa: F401
 
 __all__ = list(_api_all) + ["init", "finalize", "load", "GempicError", "ArgumentError", "AssertionFailed",
-                            "DistributedContext", "shard_range"]
+                            "DistributedContext", "shard_range", "sharded_parity"]

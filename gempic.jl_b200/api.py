@@ -17,7 +17,7 @@ __all__ = [
     "OneDGrid", "TwoDGrid", "ParticleGroup", "ParticleMeshCoupling1D", "ParticleMeshCoupling2D", "Maxwell1DFEM", "TwoDMaxwell", "HamiltonianSplitting2D3V",
     "HamiltonianSplitting", "HamiltonianSplittingBoris", "TimeHistoryDiagnostics", "strang_splitting",
     "staggering", "operatorHp1", "operatorHp2", "operatorHE", "operatorHB", "solve_poisson", "write_step",
-    "add_charge", "evaluate", "add_current_update_v", "compute_e_from_rho", "compute_e_from_j", "compute_e_from_b",
+    "add_charge", "evaluate", "add_current_update_v", "add_charge_pp", "evaluate_pp", "add_current_update_v_pp", "PPField", "compute_e_from_rho", "compute_e_from_j", "compute_e_from_b",
     "compute_b_from_e", "inner_product", "l2norm_squared", "l2projection", "compute_rhs_from_function",
     "synchronize", "launch_count", "stream_ptr", "device_info", "set_option", "DIAG_COLUMNS", "save", "load_particles",
 ]
@@ -224,6 +224,14 @@ class ParticleGroup(_Handle):
         self._host, self._host_newer, self._dev_newer = None, False, True
 
 
+class PPField:
+    """what b_to_pp (src/splinepp.jl:241-261, :392) returns here: the spline dofs behind an opaque name -- the device
+    kernels build the per-cell polynomials themselves (cell_poly, csrc/ops1d.cuh)"""
+
+    def __init__(self, dofs):
+        self.dofs = dofs
+
+
 class ParticleMeshCoupling1D(_Handle):
     """ParticleMeshCoupling1D(mesh, no_particles, spline_degree, smoothing_type)
     (src/particle_mesh_coupling_1d.jl:26-95)."""
@@ -276,6 +284,17 @@ class ParticleMeshCoupling1D(_Handle):
                                                      C.c_int64(xo.size), dptr(j_dofs)))
         return float(v[0]) if scalar else v
 
+    # the `_pp` forms of the reference (:106-250) compute the same functions through the piecewise-polynomial tables; the
+    # kernels here always evaluate in pp form, so they are aliases.  b_to_pp returns an opaque handle on the dofs.
+    add_charge_pp = add_charge
+    add_current_update_v_pp = add_current_update_v
+
+    def b_to_pp(self, field_dofs):
+        return PPField(_vec(field_dofs, self.n_dofs, "field_dofs").copy())
+
+    def evaluate_pp(self, position, field_dofs_pp):
+        return self.evaluate(position, field_dofs_pp.dofs)
+
     def add_charge_pg(self, rho_dofs, pg: ParticleGroup):
         """rho += sum_i add_charge!(rho, p, x_i, get_charge(pg, i)) on the device-resident group."""
         pg._flush()
@@ -320,6 +339,16 @@ class ParticleMeshCoupling2D(_Handle):
         check(_L().gempic_pmc2d_evaluate(self._h, dptr(x), dptr(y), C.c_int64(x.size), dptr(_vec(field_dofs, self.n_dofs, "field_dofs")),
                                          dptr(out)))
         return float(out[0]) if scalar else out
+
+    # `_pp` forms (src/particle_mesh_coupling_2d.jl:107-188): same functions through the pp tables (floor instead of ceil
+    # cell index, identical values by continuity of the splines)
+    add_charge_pp = add_charge
+
+    def b_to_pp(self, field_dofs):
+        return PPField(_vec(field_dofs, self.n_dofs, "field_dofs").copy())
+
+    def evaluate_pp(self, xp, yp, pp):
+        return self.evaluate(xp, yp, pp.dofs)
 
     def evaluate_multiple(self, position, field_dofs):
         xp, yp = position
@@ -474,12 +503,14 @@ class HamiltonianSplitting(_Handle):
     e_dofs, b_dofs) (src/hamiltonian_splitting.jl:20-86).  `e_dofs` (list of two arrays) and `b_dofs`
     are the caller's arrays: like the reference, every operator reads them on entry and leaves the
     updated values in them (the drop-in, host-buffer path).  `resident=True` switches to the
-    device-resident path: fields are uploaded once and only copied back by `sync_fields()`."""
+    device-resident path: fields are uploaded once and only copied back by `sync_fields()`.
+    `fuse=True` (the default of the library and of every front end) runs the particle passes of
+    strang_splitting! fused (same trajectory); `fuse=False` runs one pass per operator."""
 
     _destroy = "gempic_hs_destroy"
 
     def __init__(self, D, V, maxwell_solver, kernel_smoother_0, kernel_smoother_1, particle_group, e_dofs, b_dofs,
-                 resident=False):
+                 resident=False, fuse=True):
         super().__init__()
         self.dims = (D, V)
         self.maxwell_solver = maxwell_solver
@@ -494,6 +525,8 @@ class HamiltonianSplitting(_Handle):
         self.Lx, self.x_min = maxwell_solver.Lx, maxwell_solver.xmin
         self.delta_x = self.Lx / n
         self.resident = resident
+        if not fuse:
+            self.set_fusion(False)
         if resident:
             self.upload_fields()
 
@@ -827,6 +860,18 @@ def evaluate(p, *args):
 
 def add_current_update_v(j_dofs, p, *args):
     return p.add_current_update_v(j_dofs, *args)
+
+
+def add_charge_pp(rho_dofs, p, *args):
+    p.add_charge_pp(rho_dofs, *args)
+
+
+def evaluate_pp(p, *args):
+    return p.evaluate_pp(*args)
+
+
+def add_current_update_v_pp(j_dofs, p, *args):
+    return p.add_current_update_v_pp(j_dofs, *args)
 
 
 def compute_e_from_rho(e, m, rho):

@@ -430,20 +430,21 @@ int gempic_hs_create(int D, int V, gempic_handle maxwell, gempic_handle pmc0, ge
     GP_API_BEGIN
     require_init();
     GP_REQUIRE(out, GEMPIC_EINVAL, "null output handle");
-    auto h = std::make_unique<Splitting>();
-    h->maxwell = get<Maxwell1D>(maxwell, "Maxwell1DFEM");
-    h->ks0 = get<Pmc1D>(pmc0, "ParticleMeshCoupling1D");
-    h->ks1 = get<Pmc1D>(pmc1, "ParticleMeshCoupling1D");
-    h->pg = get_pg(pgh);
+    Maxwell1D *mx = get<Maxwell1D>(maxwell, "Maxwell1DFEM");
+    Pmc1D *ks0 = get<Pmc1D>(pmc0, "ParticleMeshCoupling1D"), *ks1 = get<Pmc1D>(pmc1, "ParticleMeshCoupling1D");
+    ParticleGroup *pg = get_pg(pgh);
     GP_REQUIRE(D == 1 && (V == 1 || V == 2), GEMPIC_EINVAL, "HamiltonianSplitting{%d,%d} is not defined by the reference", D, V);
-    GP_REQUIRE(h->pg->D == D && h->pg->V == V, GEMPIC_EASSERT, "dims == particle_group.dims (hamiltonian_splitting.jl:47)");
-    GP_REQUIRE(h->ks0->n_grid == h->ks1->n_grid, GEMPIC_EASSERT,
+    GP_REQUIRE(pg->D == D && pg->V == V, GEMPIC_EASSERT, "dims == particle_group.dims (hamiltonian_splitting.jl:47)");
+    GP_REQUIRE(ks0->n_grid == ks1->n_grid, GEMPIC_EASSERT,
                "kernel_smoother_0.n_dofs == kernel_smoother_1.n_dofs (hamiltonian_splitting.jl:49)");
-    GP_REQUIRE(h->ks0->n_grid == h->maxwell->n, GEMPIC_EASSERT, "kernel smoothers and Maxwell solver differ in n_dofs");
-    GP_REQUIRE(h->ks0->xmin == h->ks1->xmin && h->ks0->xmax == h->ks1->xmax, GEMPIC_EINVAL,
+    GP_REQUIRE(ks0->n_grid == mx->n, GEMPIC_EASSERT, "kernel smoothers and Maxwell solver differ in n_dofs");
+    GP_REQUIRE(ks0->xmin == ks1->xmin && ks0->xmax == ks1->xmax, GEMPIC_EINVAL,
                "both kernel smoothers must live on the same mesh");
-    h->D = D; h->V = V; h->n = h->ks0->n_grid;
-    h->pg_handle = pgh;
+    auto h = std::make_unique<Splitting>();
+    h->maxwell = mx; h->ks0 = ks0; h->ks1 = ks1; h->pg = pg;
+    retain(mx); retain(ks0); retain(ks1); retain(pg);
+    h->D = D; h->V = V; h->n = ks0->n_grid;
+    h->fuse = 1;   // the fused passes are the default in every front end (gempic_hs_set_fusion(h, 0): one pass per operator)
     h->fields.alloc((size_t)10 * h->n);
     h->fields.zero(ctx().stream);
     *out = register_object(std::move(h));
@@ -454,11 +455,7 @@ int gempic_hs_destroy(gempic_handle hs)
 {
     GP_API_BEGIN
     Splitting *h = get<Splitting>(hs, "HamiltonianSplitting");
-    try {   // a deferred HE kick must not be lost; the particle group may already be gone
-        ParticleGroup *pg = get<ParticleGroup>(h->pg_handle, "ParticleGroup");
-        if (pg->pending == h) pg_sync(*pg);
-    } catch (const Fail &) {
-    }
+    if (h->pg->pending == h) pg_sync(*h->pg);   // a deferred HE kick must not be lost (rank-local pass)
     destroy(hs, Kind::Splitting, "HamiltonianSplitting");
     GP_API_END
 }
@@ -537,16 +534,17 @@ int gempic_boris_create(gempic_handle maxwell, gempic_handle pmc0, gempic_handle
     GP_API_BEGIN
     require_init();
     GP_REQUIRE(out, GEMPIC_EINVAL, "null output handle");
-    auto s = std::make_unique<Boris>();
-    s->maxwell = get<Maxwell1D>(maxwell, "Maxwell1DFEM");
-    s->ks0 = get<Pmc1D>(pmc0, "ParticleMeshCoupling1D");
-    s->ks1 = get<Pmc1D>(pmc1, "ParticleMeshCoupling1D");
-    s->pg = get_pg(pgh);
-    GP_REQUIRE(s->pg->D == 1 && s->pg->V == 2, GEMPIC_EASSERT, "HamiltonianSplittingBoris needs a ParticleGroup{1,2}");
-    GP_REQUIRE(s->ks0->n_grid == s->ks1->n_grid && s->ks0->n_grid == s->maxwell->n, GEMPIC_EASSERT, "n_dofs mismatch");
-    GP_REQUIRE(s->ks0->xmin == s->ks1->xmin && s->ks0->xmax == s->ks1->xmax, GEMPIC_EINVAL,
+    Maxwell1D *mx = get<Maxwell1D>(maxwell, "Maxwell1DFEM");
+    Pmc1D *ks0 = get<Pmc1D>(pmc0, "ParticleMeshCoupling1D"), *ks1 = get<Pmc1D>(pmc1, "ParticleMeshCoupling1D");
+    ParticleGroup *pg = get_pg(pgh);
+    GP_REQUIRE(pg->D == 1 && pg->V == 2, GEMPIC_EASSERT, "HamiltonianSplittingBoris needs a ParticleGroup{1,2}");
+    GP_REQUIRE(ks0->n_grid == ks1->n_grid && ks0->n_grid == mx->n, GEMPIC_EASSERT, "n_dofs mismatch");
+    GP_REQUIRE(ks0->xmin == ks1->xmin && ks0->xmax == ks1->xmax, GEMPIC_EINVAL,
                "both kernel smoothers must live on the same mesh");
-    s->n = s->ks0->n_grid;
+    auto s = std::make_unique<Boris>();
+    s->maxwell = mx; s->ks0 = ks0; s->ks1 = ks1; s->pg = pg;
+    retain(mx); retain(ks0); retain(ks1); retain(pg);
+    s->n = ks0->n_grid;
     s->fields.alloc((size_t)10 * s->n);
     s->fields.zero(ctx().stream);
     *out = register_object(std::move(s));

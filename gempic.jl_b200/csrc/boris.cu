@@ -18,6 +18,14 @@ static PassParams<Op> base_params(Boris &s)
     return P;
 }
 
+Boris::~Boris()
+{
+    if (maxwell) release(maxwell);
+    if (ks0) release(ks0);
+    if (ks1) release(ks1);
+    if (pg) release(pg);
+}
+
 void boris_push_v_epart(Boris &s, double dt)   // :189-204
 {
     const double dtqm = dt * s.pg->q_over_m;

@@ -45,6 +45,7 @@ struct Context {
     // multi-GPU
     void *nccl_comm = nullptr;
     int n_ranks = 1, rank = 0;
+    int suspended_ranks = 0;   // gempic_comm_suspend: n_ranks while this rank works on its own
     double *pinned = nullptr;  // small pinned staging buffer for field I/O
     size_t pinned_bytes = 0;
 };
@@ -94,9 +95,15 @@ enum class Kind : uint32_t { ParticleGroup = 1, Pmc1D, Pmc2D, Maxwell1D, Splitti
 
 struct Object {
     Kind kind;
+    int users = 0;   // splitting objects that hold a raw pointer to this one (retain / release)
     explicit Object(Kind k) : kind(k) {}
     virtual ~Object() = default;
 };
+// Lifetime of the objects a splitting points to (its particle group, smoothers, Maxwell solver): destroying a handle
+// that is still retained only removes it from the registry; the memory goes when the last user releases it, so a
+// garbage collector may finalise the host-side wrappers in any order.
+void retain(Object *o);
+void release(Object *o);
 
 gempic_handle register_object(std::unique_ptr<Object> obj);
 Object *lookup(gempic_handle h, Kind kind, const char *what);

@@ -54,6 +54,7 @@ static void op_Hp2(Splitting &h, double dt)
         P.op.wscale0 = h.pg->charge * h.pg->common_weight * h.ks0->scaling;
         launch_pass<Op>(P, &h.scratch, h.j2(), "operatorHp2");
     });
+    h.j2_stale = h.j2_unreduced = false;   // j_dofs[2] is overwritten
     GP_CUDA(cudaMemsetAsync(h.j1(), 0, sizeof(double) * h.n, ctx().stream));   // fill!(j_dofs[1], 0) :132
     allreduce_sum(h.j2(), h.n);
     field_e_from_j(*h.maxwell, h.e2(), h.j2(), 2, dt);   // j2 .*= dt ; compute_e_from_j!(e2, j2, 2)  :173-175
@@ -78,6 +79,7 @@ static void op_Hp1(Splitting &h, double dt, bool with_rho)
             P.fields[0] = h.b();
             set_hp1_params<Op>(h, dt, P.op);
             launch_pass<Op>(P, &h.scratch, h.j1(), "operatorHp1+rho");   // j1 | j2 are adjacent: out = [j1, rho]
+            h.j2_stale = h.j2_unreduced = false;
         } else {
             using Op = OpHp1<D0, D1, false>;
             auto P = base_params<Op>(h);
@@ -131,6 +133,7 @@ static void fused_pass(Splitting &h, double dt, int n_he, double dt_T, DeferredR
     // zeroed j1 (:132) and holds dt/2 * j2b -- a deposit of the particle state this pass leaves behind, rebuilt by
     // materialise_j2() when somebody looks at it
     h.j2_stale = true;
+    h.j2_unreduced = true;
     h.j2_scale = 0.5 * dt;
 }
 
@@ -156,6 +159,9 @@ static void strang_fields(Splitting &h, bool solve, double dt, bool tail, double
 // j_dofs[2] after a fused pass = dt/2 * sum_p w v2 N(x) over the particles as the pass left them (the second Hp2 of
 // hamiltonian_splitting_1d2v.jl:141-175 deposits after the push and does not change v2).  `kick_dt` != 0 applies the
 // deferred trailing operatorHE kick in the same pass (after the deposit).
+// RANK-LOCAL: this rank's share (already scaled by dt/2) lands in j2(); Splitting::j2_unreduced stays set until a
+// collective entry point (hs_finish_j2) sums the shares.  pg_sync() -- reached from entry points that only one rank may
+// call (download, save, a finalizer) -- therefore never issues a collective.
 static void materialise_j2_pass(Splitting &h, double kick_dt)
 {
     const double ws0 = h.pg->charge * h.pg->common_weight * h.ks0->scaling;
@@ -175,14 +181,19 @@ static void materialise_j2_pass(Splitting &h, double kick_dt)
             launch_pass<Op>(P, &h.scratch, h.j2(), "j2 deposit");
         }
     });
-    allreduce_sum(h.j2(), h.n);
     field_axpby(h.j2(), 0.0, h.j2(), h.j2_scale, h.n);
     h.j2_stale = false;
 }
 
+// COLLECTIVE: j2() = the reference's j_dofs[2] on every rank.  Called by the entry points that hand j_dofs out
+// (gempic_hs_get_fields with j2 != NULL); j2_unreduced only changes inside collective calls, so all ranks agree on it.
 void hs_materialise_j2(Splitting &h)
 {
     if (h.j2_stale) materialise_j2_pass(h, 0.0);
+    if (h.j2_unreduced) {
+        allreduce_sum(h.j2(), h.n);
+        h.j2_unreduced = false;
+    }
 }
 
 // The fused pass only pays while its three lane-private grids fit in shared memory (n <~ 35 cells at
@@ -231,6 +242,15 @@ static void strang_fused(Splitting &h, double dt, int64_t steps)
     pg.pending = &h;
 }
 
+Splitting::~Splitting()
+{
+    if (pg && pg->pending == this) pg->pending = nullptr;
+    if (maxwell) release(maxwell);
+    if (ks0) release(ks0);
+    if (ks1) release(ks1);
+    if (pg) release(pg);
+}
+
 void pg_sync(ParticleGroup &pg)
 {
     if (pg.pending2d) hs2d_apply_pending(pg);
@@ -262,6 +282,7 @@ static void op_Hp111(Splitting &h, double dt)
         launch_pass<Op>(P, &h.scratch, h.j1(), "operatorHp1{1,1}");
     });
     GP_CUDA(cudaMemsetAsync(h.j2(), 0, sizeof(double) * h.n, ctx().stream));   // fill!(j_dofs[2], 0) 1d1v.jl:68
+    h.j2_stale = h.j2_unreduced = false;
     allreduce_sum(h.j1(), h.n);
     field_e_from_j(*h.maxwell, h.e1(), h.j1(), 1, 1.0);   // 1d1v.jl:96
 }

@@ -1121,6 +1121,13 @@ void hs2d_strang(Splitting2D &h, double dt, int64_t steps)
     }
 }
 
+Splitting2D::~Splitting2D()
+{
+    if (pg && pg->pending2d == this) pg->pending2d = nullptr;
+    if (maxwell) release(maxwell);
+    if (pg) release(pg);
+}
+
 void hs2d_moments(Splitting2D &h, double *out4_dev)
 {
     Context &c = ctx();
@@ -1146,16 +1153,17 @@ int gempic_hs2d_create(gempic_handle maxwell2d, gempic_handle pgh, gempic_handle
     GP_API_BEGIN
     require_init();
     GP_REQUIRE(out, GEMPIC_EINVAL, "null output handle");
-    auto h = std::make_unique<Splitting2D>();
-    h->maxwell = get<Maxwell2D>(maxwell2d, "TwoDMaxwell");
-    h->pg = get_pg(pgh);
-    GP_REQUIRE(h->pg->D == 2 && h->pg->V == 3, GEMPIC_EASSERT, "dims == (2, 3) (hamiltonian_splitting.jl:47)");
-    GP_REQUIRE(h->pg->W >= 1, GEMPIC_EASSERT, "particle group needs a weight row");
-    GP_REQUIRE(h->maxwell->s_deg_0 >= 1, GEMPIC_EINVAL, "degree");
-    GP_REQUIRE(h->maxwell->nx >= 2 * kR2 + 2 && h->maxwell->ny >= 2 * kR2 + 2, GEMPIC_EINVAL,
+    Maxwell2D *mx = get<Maxwell2D>(maxwell2d, "TwoDMaxwell");
+    ParticleGroup *pg = get_pg(pgh);
+    GP_REQUIRE(pg->D == 2 && pg->V == 3, GEMPIC_EASSERT, "dims == (2, 3) (hamiltonian_splitting.jl:47)");
+    GP_REQUIRE(pg->W >= 1, GEMPIC_EASSERT, "particle group needs a weight row");
+    GP_REQUIRE(mx->s_deg_0 >= 1, GEMPIC_EINVAL, "degree");
+    GP_REQUIRE(mx->nx >= 2 * kR2 + 2 && mx->ny >= 2 * kR2 + 2, GEMPIC_EINVAL,
                "HamiltonianSplitting{2,3} needs at least %d cells per direction", 2 * kR2 + 2);
-    h->nd = (size_t)h->maxwell->nx * h->maxwell->ny;
-    h->pg_handle = pgh;
+    auto h = std::make_unique<Splitting2D>();
+    h->maxwell = mx; h->pg = pg;
+    retain(mx); retain(pg);
+    h->nd = (size_t)mx->nx * mx->ny;
     h->fields.alloc(13 * h->nd + 16);
     h->fields.zero(ctx().stream);
     *out = register_object(std::move(h));
@@ -1166,11 +1174,7 @@ int gempic_hs2d_destroy(gempic_handle hs)
 {
     GP_API_BEGIN
     Splitting2D *h = get<Splitting2D>(hs, "HamiltonianSplitting{2,3}");
-    try {   // a deferred HE kick must not be lost; the particle group may already be gone
-        ParticleGroup *pg = get<ParticleGroup>(h->pg_handle, "ParticleGroup");
-        if (pg->pending2d == h) pg_sync(*pg);
-    } catch (const Fail &) {
-    }
+    if (h->pg->pending2d == h) pg_sync(*h->pg);   // a deferred HE kick must not be lost
     destroy(hs, Kind::Splitting2D, "HamiltonianSplitting{2,3}");
     GP_API_END
 }

@@ -152,9 +152,9 @@ void m2d_inner_product(const Maxwell2D &m, const double *c1, const double *c2, i
 struct Splitting : Object {
     static constexpr Kind kKind = Kind::Splitting;
     int D, V;
-    Maxwell1D *maxwell;
-    Pmc1D *ks0, *ks1;
-    ParticleGroup *pg;
+    Maxwell1D *maxwell = nullptr;   // retained (common.cuh)
+    Pmc1D *ks0 = nullptr, *ks1 = nullptr;
+    ParticleGroup *pg = nullptr;
     int n;
     DevBuf<double> fields;  // e1, e2, b, j1, j2, acc(3n), e1T, e2T   (10 * n)
     PartialScratch scratch;
@@ -163,9 +163,10 @@ struct Splitting : Object {
     // after a fused pass j2() is not yet the reference's j_dofs[2]: hs_materialise_j2() / pg_sync() rebuild it from the
     // particles (hs1d.cu).  j2_stale implies ParticleGroup::pending == this.
     bool j2_stale = false;
+    bool j2_unreduced = false;     // j2() holds this rank's share only; summed by hs_materialise_j2 (collective)
     double j2_scale = 0.0;
-    gempic_handle pg_handle = 0;
     Splitting() : Object(kKind) {}
+    ~Splitting() override;   // drops a pending kick registration and releases maxwell, ks0, ks1, pg (hs1d.cu)
     double *e1() { return fields.p; }
     double *e2() { return fields.p + n; }
     double *b() { return fields.p + 2 * (size_t)n; }
@@ -180,13 +181,14 @@ struct Splitting : Object {
 // HamiltonianSplittingBoris (src/hamiltonian_splitting_boris.jl:23-88)
 struct Boris : Object {
     static constexpr Kind kKind = Kind::Boris;
-    Maxwell1D *maxwell;
-    Pmc1D *ks0, *ks1;
-    ParticleGroup *pg;
+    Maxwell1D *maxwell = nullptr;   // retained
+    Pmc1D *ks0 = nullptr, *ks1 = nullptr;
+    ParticleGroup *pg = nullptr;
     int n;
     DevBuf<double> fields;  // e1, e2, b, j1, j2, e1_mid, e2_mid, b_mid, acc(2n)  (10 * n)
     PartialScratch scratch;
     Boris() : Object(kKind) {}
+    ~Boris() override;
     double *f(int which) { return fields.p + (size_t)which * n; }  // GEMPIC_F_* order
     double *acc() { return fields.p + 8 * (size_t)n; }
     Mesh1D mesh() const { return ks0->mesh(maxwell->Lx); }
@@ -195,8 +197,8 @@ struct Boris : Object {
 // HamiltonianSplitting{2,3} on TwoDMaxwell (hs2d.cu)
 struct Splitting2D : Object {
     static constexpr Kind kKind = Kind::Splitting2D;
-    Maxwell2D *maxwell;
-    ParticleGroup *pg;
+    Maxwell2D *maxwell = nullptr;   // retained
+    ParticleGroup *pg = nullptr;
     size_t nd = 0;             // nx * ny
     DevBuf<double> fields;     // e1 e2 e3 b1 b2 b3 j1 j2 j3 rho e1T e2T e3T (13 * nd) + 16 scalars
     int fuse = 1;              // fused [HE,Hp3] pass and cross-step HE fold inside strang_splitting
@@ -204,8 +206,8 @@ struct Splitting2D : Object {
     int sort_interval = 1;     // cell-sort every k Strang steps (0: never)
     int64_t steps_done = 0;
     double pending_dt = 0.0;   // dt of the deferred trailing HE kick (ParticleGroup::pending2d == this; fields in eT)
-    gempic_handle pg_handle = 0;
     Splitting2D() : Object(kKind) {}
+    ~Splitting2D() override;
     double *e(int c) { return fields.p + (size_t)c * nd; }
     double *b(int c) { return fields.p + (size_t)(3 + c) * nd; }
     double *j(int c) { return fields.p + (size_t)(6 + c) * nd; }

@@ -65,6 +65,29 @@ Object *lookup(gempic_handle h, Kind kind, const char *what)
     return it->second.get();
 }
 
+static std::vector<std::unique_ptr<Object>> g_zombies;   // destroyed handles that a splitting object still points to
+
+void retain(Object *o)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    o->users++;
+}
+
+void release(Object *o)
+{
+    std::unique_ptr<Object> victim;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (--o->users > 0) return;
+        for (auto it = g_zombies.begin(); it != g_zombies.end(); ++it)
+            if (it->get() == o) {
+                victim = std::move(*it);
+                g_zombies.erase(it);
+                break;
+            }
+    }
+}
+
 void destroy(gempic_handle h, Kind kind, const char *what)
 {
     std::unique_ptr<Object> victim;
@@ -75,14 +98,36 @@ void destroy(gempic_handle h, Kind kind, const char *what)
             fail(GEMPIC_EHANDLE, "invalid %s handle 0x%llx", what, (unsigned long long)h);
         victim = std::move(it->second);
         g_objects.erase(it);
+        if (victim->users > 0) g_zombies.push_back(std::move(victim));
     }
     if (g_ctx.ready) cudaStreamSynchronize(g_ctx.stream);
-}
+}   // `victim` (and, through its destructor, the releases of what it retained) goes here, outside the lock
 
 void destroy_all()
 {
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_objects.clear();
+    // the splitting objects first: their destructors release the objects they point to
+    std::vector<std::unique_ptr<Object>> doomed;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (auto it = g_objects.begin(); it != g_objects.end();) {
+            const Kind k = it->second->kind;
+            if (k == Kind::Splitting || k == Kind::Boris || k == Kind::Splitting2D) {
+                doomed.push_back(std::move(it->second));
+                it = g_objects.erase(it);
+            } else {
+                ++it;
+            }
+        }
+    }
+    doomed.clear();
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (auto &kv : g_objects) doomed.push_back(std::move(kv.second));
+        g_objects.clear();
+        for (auto &z : g_zombies) doomed.push_back(std::move(z));
+        g_zombies.clear();
+    }
+    doomed.clear();
 }
 
 // ---- staging ---------------------------------------------------------------------------
@@ -458,11 +503,32 @@ int gempic_comm_finalize(void)
         c.nccl_comm = nullptr;
     }
     c.n_ranks = 1;
+    c.suspended_ranks = 0;
     c.rank = 0;
     GP_API_END
 }
 
 int gempic_comm_size(void) { return ctx().n_ranks; }
+
+/* suspend = 1: the communicator stays alive but this rank works on its own (every all-reduce is skipped, the single-GPU
+ * launch sequences are used) until suspend = 0.  For un-sharded reference runs next to a sharded one (bench.py's
+ * sharded_parity, tests/dist_worker.py); every rank must resume before the next collective. */
+int gempic_comm_suspend(int suspend)
+{
+    GP_API_BEGIN
+    require_init();
+    Context &c = ctx();
+    if (suspend && !c.suspended_ranks && c.nccl_comm) {
+        GP_CUDA(cudaStreamSynchronize(c.stream));
+        c.suspended_ranks = c.n_ranks;
+        c.n_ranks = 1;
+    } else if (!suspend && c.suspended_ranks) {
+        GP_CUDA(cudaStreamSynchronize(c.stream));
+        c.n_ranks = c.suspended_ranks;
+        c.suspended_ranks = 0;
+    }
+    GP_API_END
+}
 
 int gempic_comm_allreduce(double *host_inout, int64_t n)
 {

@@ -77,6 +77,9 @@ int gempic_comm_unique_id(void *id128);
 int gempic_comm_init(int n_ranks, int rank, const void *id128);
 int gempic_comm_finalize(void);
 int gempic_comm_size(void);
+/* suspend = 1: keep the communicator but let this rank work on its own (all-reduces skipped) until suspend = 0 --
+ * for an un-sharded check run next to a sharded one.  Every rank must resume before the next collective call. */
+int gempic_comm_suspend(int suspend);
 /* test hook: all-reduce (sum) a host vector through the same path the operators use */
 int gempic_comm_allreduce(double *host_inout, int64_t n);
 
@@ -96,8 +99,8 @@ int gempic_pg_get_row_device(gempic_handle pg, int row, double *dev_dst);
 int gempic_pg_row_ptr(gempic_handle pg, int row, double **dev_ptr);
 int gempic_pg_info(gempic_handle pg, int *D, int *V, int *n_weights, int64_t *n_particles,
                    double *charge, double *mass, double *common_weight);
-/* Periodic counting sort of the SoA rows by cell of x1 (and x2 for D=2) on the mesh of `pmc`.
- * Stable. If `perm_out_dev` != NULL it receives, per sorted slot, the previous index. */
+/* Periodic counting sort of the SoA rows by cell of x1 on the mesh of `pmc` (D = 1; gempic_pg_sort2d for D = 2).
+ * Stable: particles of one cell keep their relative order. */
 int gempic_pg_sort(gempic_handle pg, gempic_handle pmc);
 /* Device-side synthetic loads: counter-based RNG, seed 1234 default.
  * kind 0: x ~ U[0,L), v ~ N(0, sigma_k); kind 1: Landau x by inverse CDF of 1+alpha*cos(kx).
@@ -202,7 +205,7 @@ int gempic_hs_operator_host(gempic_handle hs, int op, double dt, double *e1, dou
 int gempic_hs_strang_splitting_host(gempic_handle hs, double dt, int64_t number_steps, double *e1, double *e2,
                                     double *b, double *j1, double *j2);
 /* Same trajectory with the particle passes of a Strang step fused:
- * fuse = 0 one kernel per reference operator (default), 1 fused [HE,Hp2,Hp1,Hp2] pass. */
+ * fuse = 1 (default, in every front end) fused [HE,Hp2,Hp1,Hp2] pass, 0 one kernel per reference operator. */
 int gempic_hs_set_fusion(gempic_handle hs, int fuse);
 
 /* ---- HamiltonianSplitting{2,3} on TwoDMaxwell (BASELINE config 5) ---------------------------

@@ -1002,6 +1002,16 @@ int orc_sizeof(int what)
     default: return -1;
     }
 }
+/* pin the OpenMP team size explicitly (bench.py: an inherited OMP_NUM_THREADS=1 under torchrun must not shrink the
+ * CPU arm silently) */
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

@@ -369,3 +369,9 @@ class ParticleMeshCoupling2D:
 
 def max_threads() -> int:
     return lib().orc_max_threads()
+
+
+def set_threads(n: int) -> int:
+    """omp_set_num_threads(n); returns the team size now in force (1 without OpenMP)"""
+    lib().orc_set_threads(C.c_int(int(n)))
+    return lib().orc_max_threads()

@@ -6,7 +6,9 @@ mode gloo : host-side logic of the sharded path -- index-range sharding, unique-
             max-over-ranks timing.  No GPU needed.
 mode nccl : the real thing -- every rank owns a shard of the particles on its GPU, libgempic_b200
             all-reduces the grid moments with NCCL; the result must equal the 1-rank run of the
-            full set computed by rank 0 on its own GPU with a second, un-sharded group.
+            full set computed by rank 0 on its own GPU with a second, un-sharded group.  Covers
+            HamiltonianSplitting{1,2} (fused / un-fused), HamiltonianSplittingBoris (fused step / separate
+            pushes) and HamiltonianSplitting{2,3} (fused / un-fused) -- BASELINE configs 3, 4, 5.
 """
 import json
 import math
@@ -71,51 +73,10 @@ def run_nccl(out_path):
     dc = gp.DistributedContext(backend="nccl")
     assert dc.world_size >= 2 and torch.cuda.device_count() >= dc.world_size
     dc.init_library_comm()
-    n, nx, L = 400_003, 32, 4 * math.pi
-    state = landau_state(n, L, seed=7)
-    first, count = dc.shard(n)
-
-    def build(cols, n_global):
-        mesh = gp.OneDGrid(0.0, L, nx)
-        pg = gp.ParticleGroup(1, 2, cols.shape[1], common_weight=1.0 / n_global)
-        pg.upload(np.ascontiguousarray(cols))
-        ks0 = gp.ParticleMeshCoupling1D(mesh, n_global, 3, "galerkin")
-        ks1 = gp.ParticleMeshCoupling1D(mesh, n_global, 2, "galerkin")
-        mx = gp.Maxwell1DFEM(mesh, 3)
-        e1, e2, rho = np.zeros(nx), np.zeros(nx), np.zeros(nx)
-        b = 1e-2 * np.cos(2 * math.pi * (np.arange(nx) + 0.5) / nx)
-        return pg, ks0, ks1, mx, e1, e2, b, rho
-
-    res = {}
-    for fuse in (0, 1):
-        pg, ks0, ks1, mx, e1, e2, b, rho = build(state[:, first:first + count], n)
-        gp.solve_poisson(e1, pg, ks0, mx, rho)          # all-reduced rho -> replicated e1
-        h = gp.HamiltonianSplitting(1, 2, mx, ks0, ks1, pg, [e1, e2], b)
-        h.set_fusion(bool(fuse))
-        h.strang_splitting(0.05, 3)
-        res[fuse] = (e1.copy(), e2.copy(), b.copy(), pg.to_host())
-        # replicas agree bitwise (all-reduce result is identical on all ranks)
-        for f in (e1, e2, b):
-            ref = dc.broadcast_bytes(f.tobytes() if dc.rank == 0 else None, f.nbytes, src=0)
-            assert ref == f.tobytes(), "replicated fields drifted between ranks"
+    errs = gp.sharded_parity(dc)
     dc.barrier()
-    ok = True
-    errs = {}
-    # every rank leaves the communicator together; rank 0 then repeats the run un-sharded
     dc.finalize()
     if dc.rank == 0:
-        for fuse in (0, 1):
-            pg, ks0, ks1, mx, e1, e2, b, rho = build(state, n)
-            gp.solve_poisson(e1, pg, ks0, mx, rho)
-            h = gp.HamiltonianSplitting(1, 2, mx, ks0, ks1, pg, [e1, e2], b)
-            h.set_fusion(bool(fuse))
-            h.strang_splitting(0.05, 3)
-            full = pg.to_host()
-            r = res[fuse]
-            errs[f"e1_{fuse}"] = rel_err(r[0], e1)
-            errs[f"e2_{fuse}"] = rel_err(r[1], e2)
-            errs[f"b_{fuse}"] = rel_err(r[2], b)
-            errs[f"particles_{fuse}"] = max(rel_err(r[3][k], full[k, first:first + count]) for k in range(1, 3))
         ok = all(v < 1e-11 for v in errs.values())
         json.dump({"ok": ok, "world_size": dc.world_size, "errs": errs}, open(out_path, "w"))
         assert ok, errs

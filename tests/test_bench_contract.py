@@ -47,3 +47,16 @@ def test_reference_arm_under_torchrun_env_prints_on_rank0_only():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_ignores_an_inherited_omp_num_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm pins its team to the host's cores itself"""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--cpu-particles", "40000"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    want = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == want, (d["cpu_baseline"]["cores"], want)
+    if want > 1:
+        assert d["cpu_baseline"]["value_1_thread"] > 0

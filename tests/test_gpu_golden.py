@@ -64,6 +64,14 @@ def test_pmc1d_evaluate(gp):
     ref = golden(T1D, 137) / mesh.xmax
     assert np.max(np.abs(vals - ref)) < 1e-15  # :143
     assert np.max(np.abs(kernel.evaluate_pg(pg, rho) - ref)) < 1e-15
+    # the `_pp` entry points (pmc1d.jl:106-122,242-250) are held to the same goldens by the reference (:57-65,137-144)
+    pp = kernel.b_to_pp(rho)
+    vals_pp = np.array([gp.evaluate_pp(kernel, pg.get_x(i)[0], pp) for i in range(n_particles)])
+    assert np.max(np.abs(vals_pp - ref)) < 1e-15
+    rho_pp = np.zeros(n_cells)
+    for i in range(n_particles):
+        gp.add_charge_pp(rho_pp, kernel, pg.get_x(i)[0], pg.get_charge(i))
+    assert np.max(np.abs(rho_pp - rho)) < 1e-15
 
 
 def test_pmc2d(gp):
@@ -177,6 +185,18 @@ def test_boris(gp):
     # convolution form of the circulant solve
     assert np.max(np.abs(e1 - e_ref[0])) < 2e-15
     assert np.max(np.abs(e2 - e_ref[1])) < 1e-15
+
+
+@pytest.mark.parametrize("n,deg,L", [(32, 3, 4 * math.pi), (256, 3, 2 * math.pi), (20, 2, 1.7), (8, 1, 3.0)])
+def test_maxwell1d_tables_match_oracle(gp, orc, n, deg, L):
+    """Maxwell1DFEM constructor tables (maxwell_1d_fem.jl:60-153: eig_mass0/1, eig_weak_ampere, eig_weak_poisson in the
+    FFTW half-complex layout) read back through gempic_maxwell1d_get_table, against the CPU restatement"""
+    mg = gp.Maxwell1DFEM(gp.OneDGrid(0.25, 0.25 + L, n), deg)
+    mo = orc.Maxwell1DFEM(orc.OneDGrid(0.25, 0.25 + L, n), deg)
+    for name in ("eig_mass0", "eig_mass1", "eig_weak_ampere", "eig_weak_poisson"):
+        a, b = getattr(mg, name), getattr(mo, name)
+        assert a.shape == b.shape == (n,)
+        assert np.max(np.abs(a - b)) <= 4e-16 * max(1.0, np.max(np.abs(b))), name
 
 
 def test_maxwell1d_analytic(gp):

@@ -40,6 +40,10 @@ def test_field_operators_match_oracle(gp, nx, ny, deg):
     for a in range(2):
         assert np.allclose(mg.mass_line_0[a], mo.mass_line_0[a], rtol=1e-15, atol=0)
         assert np.allclose(mg.mass_line_1[a], mo.mass_line_1[a], rtol=1e-15, atol=0)
+        # spline_fem_compute_mass_eig of those lines (maxwell_2d_fem.jl:51-54, poisson_2d_fem.jl:113-126)
+        nn = (nx, ny)[a]
+        assert np.allclose(mg._table(2, a), m2.spline_fem_compute_mass_eig(nn, deg, mo.mass_line_0[a]), rtol=1e-14, atol=0)
+        assert np.allclose(mg._table(3, a), m2.spline_fem_compute_mass_eig(nn, deg - 1, mo.mass_line_1[a]), rtol=1e-14, atol=0)
     # mass multiply / solve for every (component, form)
     c = rng.normal(size=n)
     for form in (1, 2):

@@ -49,12 +49,13 @@ def test_operators_1d2v(orc, gp, n, nx):
 
 @pytest.mark.parametrize("deg0,deg1", [(3, 2), (3, 3), (2, 1), (2, 2), (1, 0), (1, 1)])
 @pytest.mark.parametrize("smoothing", ["galerkin", "collocation"])
-def test_strang_all_degrees(orc, gp, deg0, deg1, smoothing):
+@pytest.mark.parametrize("fuse", [False, True])
+def test_strang_all_degrees(orc, gp, deg0, deg1, smoothing, fuse):
     n = 40_000
     state = weibel_state(n, L_WEIBEL, seed=deg0 * 10 + deg1)
     so, sg = both(orc, gp, state, L_WEIBEL, nx=32, deg0=deg0, deg1=deg1, smoothing=smoothing)
     so.init_fields(b_amp=1e-2, e2_amp=1e-3), sg.init_fields(b_amp=1e-2, e2_amp=1e-3)
-    ho, hg = so.splitting(), sg.splitting()
+    ho, hg = so.splitting(), sg.splitting(fuse=fuse)
     ho.strang_splitting(0.05, 3)
     hg.strang_splitting(0.05, 3)
     assert particle_err(sg.particles(), so.particles(), L_WEIBEL) < 1e-11  # 3 steps of chaotic amplification
@@ -101,8 +102,7 @@ def test_strang_fused_equals_unfused_long_run(gp):
     n = 200_000
     state = landau_state(n, L_LANDAU, seed=21)
     sa, sb = Sim1D(gp, state, L_LANDAU).init_fields(), Sim1D(gp, state, L_LANDAU).init_fields()
-    ha, hb = sa.splitting(resident=True), sb.splitting(resident=True)
-    hb.set_fusion(True)
+    ha, hb = sa.splitting(resident=True, fuse=False), sb.splitting(resident=True, fuse=True)
     ha.strang_splitting(0.05, 200)
     hb.strang_splitting(0.05, 200)
     ha.sync_fields(), hb.sync_fields()
