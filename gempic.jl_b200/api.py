@@ -19,6 +19,7 @@ __all__ = [
     "staggering", "operatorHp1", "operatorHp2", "operatorHE", "operatorHB", "solve_poisson", "write_step",
     "add_charge", "evaluate", "add_current_update_v", "add_charge_pp", "evaluate_pp", "add_current_update_v_pp", "PPField", "compute_e_from_rho", "compute_e_from_j", "compute_e_from_b",
     "compute_b_from_e", "inner_product", "l2norm_squared", "l2projection", "compute_rhs_from_function",
+    "ParticleSampler", "CosSumGaussian", "SumCosGaussian", "LandauDamping", "sample",
     "synchronize", "launch_count", "stream_ptr", "device_info", "set_option", "DIAG_COLUMNS", "save", "load_particles",
 ]
 
@@ -764,6 +765,103 @@ class HamiltonianSplittingBoris(_Handle):
 
     def push_x_accumulate_j(self, dt):
         self._push("gempic_boris_push_x_accumulate_j", dt)
+
+
+# ---- samplers (src/particle_sampling.jl, src/distributions.jl, src/landau_damping.jl) ---------------------------------
+class _CosGaussian:
+    """parameters of CosSumGaussian{D,V} / SumCosGaussian{D,V} (src/distributions.jl:13-157); k: one wave vector per
+    cosine, alpha: strengths, sigma / mu: one velocity vector per Gaussian, delta: portions"""
+
+    def __init__(self, D, V, k, alpha, sigma, mu, delta=(1.0,)):
+        self.dims = (int(D), int(V))
+        self.k = [np.atleast_1d(np.asarray(kk, dtype=np.float64)) for kk in k]
+        self.alpha = np.asarray(alpha, dtype=np.float64)
+        self.sigma = [np.atleast_1d(np.asarray(x, dtype=np.float64)) for x in sigma]
+        self.mu = [np.atleast_1d(np.asarray(x, dtype=np.float64)) for x in mu]
+        self.delta = np.asarray(delta, dtype=np.float64)
+        self.n_cos, self.n_gaussians = len(self.k), len(self.sigma)
+        if self.n_cos != len(self.alpha) or any(len(kk) != D for kk in self.k):
+            raise _lib.AssertionFailed(2, "n_cos == length(alpha), length(k[i]) == dims[1] (distributions.jl:32-35)")
+        if self.n_gaussians != len(self.mu) or any(len(x) != V for x in self.sigma) or any(np.any(x == 0.0) for x in self.sigma):
+            raise _lib.AssertionFailed(2, "n_gaussians == length(mu), all(sigma .!= 0.0) (distributions.jl:36-41)")
+        if float(np.sum(self.delta)) != 1.0 or len(self.delta) != self.n_gaussians:
+            raise _lib.AssertionFailed(2, "sum(delta) == 1.0 (distributions.jl:44)")
+
+    def eval_x_density(self, x):
+        x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+        return 1.0 + sum(a * np.cos(np.sum(kk * x)) for a, kk in zip(self.alpha, self.k))
+
+
+class CosSumGaussian(_CosGaussian):
+    """CosSumGaussian{D,V}(k, alpha, sigma, mu, delta) (src/distributions.jl:88-107)"""
+
+
+class SumCosGaussian(_CosGaussian):
+    """SumCosGaussian{D,V}(k, alpha, sigma, mu, delta) (src/distributions.jl:142-157)"""
+
+
+class LandauDamping:
+    """LandauDamping(alpha, kx) (src/landau_damping.jl:10-13)"""
+
+    def __init__(self, alpha, kx):
+        self.alpha, self.kx = float(alpha), float(kx)
+
+
+class ParticleSampler:
+    """ParticleSampler{D,V}(sampling_type, symmetric, n_particles, seed = 1234) (src/particle_sampling.jl:14-59);
+    sampling_type "random" or "sobol"."""
+
+    def __init__(self, D, V, sampling_type, symmetric, n_particles, seed=1234):
+        if sampling_type not in ("random", "sobol"):
+            raise _lib.ArgumentError(1, f"Sampling type {sampling_type} not implemented")
+        n_particles = int(n_particles)
+        if symmetric:   # :33-38 (sic: the remainder is added)
+            rem = n_particles % 2 ** (D + V)
+            if rem != 0:
+                n_particles += rem
+        self.sampling_type, self.dims, self.n_particles = sampling_type, (int(D), int(V)), n_particles
+        self.symmetric, self.seed = bool(symmetric), int(seed)
+
+
+def sample(pg, *args, first_index=0, n_global=None):
+    """sample!(pg, ps::ParticleSampler, df, mesh)            src/particle_sampling.jl:68-77 ({1,2}), :248-256 ({1,1})
+    sample!(pg, alpha, k, sigma, mesh)                     :266-311  (Sobol(2) + Newton Landau load)
+    sample!(d::LandauDamping, pg) -- called as sample(d, pg) -- src/landau_damping.jl:34-59
+    on the device.  `first_index` / `n_global`: this group holds the particles first_index .. of a load of n_global
+    (sharded runs; the load does not depend on the sharding)."""
+    if isinstance(pg, LandauDamping):
+        d, pg = pg, args[0]
+        n_global = pg.n_particles if n_global is None else n_global
+        _sample_landau(pg, d.alpha, d.kx, 1.0, 2 * np.pi / d.kx / n_global, first_index, n_global)
+        return
+    n_global = pg.n_particles if n_global is None else n_global
+    if isinstance(args[0], ParticleSampler):
+        ps, df, mesh = args
+        if pg.dims == (1, 1):   # :248-256
+            _sample_landau(pg, float(df.alpha[0]), float(df.k[0][0]), float(df.sigma[0][0]), mesh.dimx, first_index, n_global)
+            return
+        if pg.dims != (1, 2):
+            raise _lib.ArgumentError(1, "sample! is defined for ParticleGroup{1,1} and {1,2}")
+        kk = np.ascontiguousarray([x[0] for x in df.k], dtype=np.float64)
+        al = np.ascontiguousarray(df.alpha, dtype=np.float64)
+        sg = np.ascontiguousarray(np.stack(df.sigma), dtype=np.float64)
+        mu = np.ascontiguousarray(np.stack(df.mu), dtype=np.float64)
+        de = np.ascontiguousarray(df.delta, dtype=np.float64)
+        check(_L().gempic_pg_sample_cos_gaussian(pg.handle, C.c_int(1 if ps.sampling_type == "sobol" else 0),
+                                                 C.c_int(1 if ps.symmetric else 0), C.c_uint64(ps.seed), _f(mesh.xmin), _f(mesh.dimx),
+                                                 C.c_int(df.n_cos), dptr(kk), dptr(al), C.c_int(df.n_gaussians), dptr(sg), dptr(mu),
+                                                 dptr(de), C.c_int64(first_index)))
+        pg._host, pg._host_newer, pg._dev_newer = None, False, True
+        return
+    alpha, k, sigma, mesh = args
+    if pg.dims == (1, 2) and not np.isclose(mesh.dimx, 2 * np.pi / k):
+        raise _lib.AssertionFailed(2, "mesh.dimx ≈ 2π / k (particle_sampling.jl:297)")
+    _sample_landau(pg, alpha, k, sigma, mesh.dimx, first_index, n_global)
+
+
+def _sample_landau(pg, alpha, k, sigma, weight, first_index, n_global):
+    check(_L().gempic_pg_sample_landau(pg.handle, _f(alpha), _f(k), _f(sigma), _f(weight), C.c_int64(first_index), C.c_int64(n_global)))
+    pg._host, pg._host_newer, pg._dev_newer = None, False, True
 
 
 DIAG_COLUMNS = ("Time", "KineticEnergy", "Momentum1", "Momentum2", "PotentialEnergyE1", "PotentialEnergyE2",

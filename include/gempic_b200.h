@@ -108,6 +108,28 @@ int gempic_pg_sort(gempic_handle pg, gempic_handle pmc);
 int gempic_pg_sample(gempic_handle pg, int kind, double xmin, double L, double alpha, double k,
                      const double *sigma, uint64_t seed, int64_t first_index);
 
+/* The reference's samplers on the device (csrc/sampling.cu).  The Sobol coordinates are those of Sobol.jl's
+ * SobolSeq (Gray-code order, Joe-Kuo direction numbers, point 0 skipped), evaluated from the GLOBAL particle index:
+ * any sharding of the index range gives the same load.
+ * sample!(pg::ParticleGroup{1,1} / {1,2}, alpha, k, sigma, mesh) (src/particle_sampling.jl:266-311): weight = mesh.dimx;
+ * sample!(d::LandauDamping, pg) (src/landau_damping.jl:34-59): sigma = 1, weight = 2 pi / kx / nbpart.
+ * Deterministic: v_i = sigma sqrt(-2 log((i - 1/2)/N)), (r1, r2) = Sobol(2), theta = 2 pi r1, x = newton(r2).
+ * n_global <= 0: this group holds all particles. */
+int gempic_pg_sample_landau(gempic_handle pg, double alpha, double k, double sigma, double weight, int64_t first_index,
+                            int64_t n_global);
+/* sample!(pg::ParticleGroup{1,2}, ps::ParticleSampler, df::AbstractCosGaussian, mesh) (src/particle_sampling.jl:68-225).
+ * sampling_type 0 :random, 1 :sobol; symmetric 0 sample_all (:89-143), 1 sample_sym (:150-225, 8-fold antithetic).
+ * df: n_cos wave numbers k / strengths alpha, n_gaussians x (sigma[2], mu[2]) row-major, portions delta (NULL for one
+ * Gaussian) -- CosSumGaussian and SumCosGaussian share eval_x_density (src/distributions.jl:159-178).
+ * Normal deviates (and the :random uniforms) come from a counter-based generator keyed by (seed, global index): Julia's
+ * MersenneTwister stream is not reproducible outside Julia -- statistical parity, exact antithetic structure.
+ * first_index must be a multiple of 8 for symmetric sampling. */
+int gempic_pg_sample_cos_gaussian(gempic_handle pg, int sampling_type, int symmetric, uint64_t seed, double xmin,
+                                  double dimx, int n_cos, const double *k, const double *alpha, int n_gaussians,
+                                  const double *sigma, const double *mu, const double *delta, int64_t first_index);
+/* test hook: points first+1 .. first+n of SobolSeq(dims) as Sobol.next! returns them (row-major n x dims, dims <= 4) */
+int gempic_sobol_points(int dims, int64_t first, int64_t n, double *out);
+
 /* ---- ParticleMeshCoupling1D (src/particle_mesh_coupling_1d.jl:26-95) ------------------ */
 int gempic_pmc1d_create(double xmin, double xmax, int n_grid, int64_t no_particles, int spline_degree,
                         int smoothing_type, gempic_handle *out);
