@@ -621,8 +621,10 @@ class HamiltonianSplitting2D3V(_Handle):
     def set_sort_interval(self, interval: int):
         check(_L().gempic_hs2d_set_sort_interval(self._h, C.c_int(interval)))
 
-    def set_fusion(self, fuse: bool):
-        check(_L().gempic_hs2d_set_fusion(self._h, C.c_int(1 if fuse else 0)))
+    def set_fusion(self, fuse):
+        """True / 2: fused passes + sorted fast path (default); 1: fused [HE,Hp3] tile pass only; False / 0: per operator"""
+        level = 2 if fuse is True else int(fuse)
+        check(_L().gempic_hs2d_set_fusion(self._h, C.c_int(level)))
 
     def _op(self, op, dt):
         pg = self.particle_group

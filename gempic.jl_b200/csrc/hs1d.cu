@@ -204,7 +204,11 @@ static bool fused_fits(Splitting &h)
     GP_DISPATCH_DEGREES(h.ks0->degree, h.ks1->degree, {
         using Op = OpStrangFused<D0, D1, 2>;
         auto P = base_params<Op>(h);
-        ok = plan_pass(P).lane_private;
+        try {
+            ok = plan_pass(P).lane_private;
+        } catch (const Fail &) {   // the pp tables alone exceed shared memory: one pass per operator
+            ok = false;
+        }
     });
     return ok;
 }

@@ -779,6 +779,445 @@ __global__ void __launch_bounds__(kThreads2, 3) k2_pass(const __grid_constant__ 
     }
 }
 
+// =====================================================================================================
+// Sorted fast path (k2_sorted): the operators that START from the cell-sorted particle order.
+//
+// What bounds k2_pass is the shared-memory pipe (ncu r01z: l1tex data-pipe wavefronts 78-85 % of peak): every gathered
+// dof is an LDS.64 (2 wavefronts per warp even when all lanes read the same word) and every deposited dof a
+// lane-private LDS + STS (4 wavefronts).  Right after the riding sort, however, the 32 lanes of a warp -- and both
+// particles every lane holds -- sit in the SAME cell for hundreds of iterations (64x64 cells, 1.25e8 particles: 30 000
+// per cell).  So for the operators that act before the particles drift apart again --
+//     [HE x NHE, Hp3, Hp2]  the head of a Strang step (trailing HE of the previous step folded in), and
+//     [Hp3]                 its tail (Hp3 follows the sorting Hp2 and does not move anybody) --
+//   * the fields come from a per-cell table in GLOBAL memory (k2_build_celltab: the cell polynomials of E1, E2, E3
+//     (kick factors folded in), B1, B2 -- b_to_pp_2d, splinepp.jl:329-392 -- and the dof stencils of B3, B1 that the
+//     y-push can reach), read with warp-uniform 128-bit loads: one L1 wavefront per two coefficients for 64 particles;
+//   * the deposits accumulate in REGISTERS across the whole cell run (j3: (D0+1)^2 dofs of the cell; j2: the D0+1 x-dofs
+//     times the D1+3 y-dofs a push of at most one cell can touch, the per-particle window shifted by selects) and are
+//     flushed -- warp-reduced, one RED per dof -- when the warp's cell changes;
+//   * no shared memory at all.
+// An iteration whose 64 particles are not all in one cell (cell-run boundaries, chunk tails) or move more than one cell
+// takes the general per-particle path (global loads and REDs), which handles anything.
+// =====================================================================================================
+template <int D0>
+struct CellTab {
+    static constexpr int D1 = D0 - 1, NX0 = D0 + 1, NX1 = D1 + 1, ROWS = D1 + 3;
+    static constexpr int even(int n) { return (n + 1) & ~1; }
+    static constexpr int O_E1 = 0;                                // x-degree D1, y-degree D0: c[j * NX1 + i]
+    static constexpr int O_E2 = O_E1 + even(NX1 * NX0);           // x-degree D0, y-degree D1: c[j * NX0 + i]
+    static constexpr int O_E3 = O_E2 + even(NX0 * NX1);           // D0 x D0
+    static constexpr int O_B1 = O_E3 + even(NX0 * NX0);           // like E2
+    static constexpr int O_B2 = O_B1 + even(NX0 * NX1);           // like E1
+    static constexpr int O_S3 = O_B2 + even(NX1 * NX0);           // B3 dofs: rows cy-1-D1 .. cy+1, cols cx-D1 .. cx
+    static constexpr int O_S1 = O_S3 + even(ROWS * NX1);          // B1 dofs: same rows, cols cx-D0 .. cx
+    static constexpr int N = O_S1 + even(ROWS * NX0);             // doubles per cell (even: 16-byte aligned sections)
+};
+
+struct CellTabParams {
+    const double *e[3], *eT[3], *b[3];
+    double dtqm_e[2];
+    int nx, ny, nhe;
+    double *out;
+};
+
+// cell polynomial of a tensor-product spline field: c[j * (DX+1) + i] = coefficient of tx^i ty^j in cell (cx, cy)
+template <int DX, int DY, class F>
+__device__ __forceinline__ void cell_poly2(int cx, int cy, int nx, int ny, F dof, double *c)
+{
+#pragma unroll
+    for (int q = 0; q < (DX + 1) * (DY + 1); ++q) c[q] = 0.0;
+#pragma unroll
+    for (int b = 0; b <= DY; ++b) {
+        const int gy = wrapi(cy - DY + b, ny);
+#pragma unroll
+        for (int a = 0; a <= DX; ++a) {
+            const double d = dof((size_t)wrapi(cx - DX + a, nx) + (size_t)gy * nx);
+#pragma unroll
+            for (int j = 0; j <= DY; ++j)
+#pragma unroll
+                for (int i = 0; i <= DX; ++i) c[j * (DX + 1) + i] = fma(d, pp_coef<DX>(a, i) * pp_coef<DY>(b, j), c[j * (DX + 1) + i]);
+        }
+    }
+}
+
+template <int D0>
+__global__ void __launch_bounds__(128) k2_build_celltab(const CellTabParams P)
+{
+    using T = CellTab<D0>;
+    constexpr int D1 = T::D1;
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= P.nx * P.ny) return;
+    const int cy = cell / P.nx, cx = cell - cy * P.nx;
+    double *o = P.out + (size_t)cell * T::N;
+    double c[(D0 + 1) * (D0 + 1)];
+    if (P.nhe > 0) {
+        auto ef = [&](int k) {
+            return [&, k](size_t g) {
+                double v = P.dtqm_e[0] * P.e[k][g];
+                if (P.nhe == 2) v = fma(P.dtqm_e[1], P.eT[k][g], v);
+                return v;
+            };
+        };
+        cell_poly2<D1, D0>(cx, cy, P.nx, P.ny, ef(0), c);
+        for (int q = 0; q < T::NX1 * T::NX0; ++q) o[T::O_E1 + q] = c[q];
+        cell_poly2<D0, D1>(cx, cy, P.nx, P.ny, ef(1), c);
+        for (int q = 0; q < T::NX0 * T::NX1; ++q) o[T::O_E2 + q] = c[q];
+        cell_poly2<D0, D0>(cx, cy, P.nx, P.ny, ef(2), c);
+        for (int q = 0; q < T::NX0 * T::NX0; ++q) o[T::O_E3 + q] = c[q];
+    }
+    cell_poly2<D0, D1>(cx, cy, P.nx, P.ny, [&](size_t g) { return P.b[0][g]; }, c);
+    for (int q = 0; q < T::NX0 * T::NX1; ++q) o[T::O_B1 + q] = c[q];
+    cell_poly2<D1, D0>(cx, cy, P.nx, P.ny, [&](size_t g) { return P.b[1][g]; }, c);
+    for (int q = 0; q < T::NX1 * T::NX0; ++q) o[T::O_B2 + q] = c[q];
+    for (int r = 0; r < T::ROWS; ++r) {
+        const size_t gy = (size_t)wrapi(cy - 1 - D1 + r, P.ny) * P.nx;
+        for (int a = 0; a <= D1; ++a) o[T::O_S3 + r * T::NX1 + a] = P.b[2][wrapi(cx - D1 + a, P.nx) + gy];
+        for (int a = 0; a <= D0; ++a) o[T::O_S1 + r * T::NX0 + a] = P.b[0][wrapi(cx - D0 + a, P.nx) + gy];
+    }
+}
+
+// N doubles (N even, 16-byte aligned, warp-uniform address) into registers
+template <int N>
+__device__ __forceinline__ void ldg_uniform(const double *__restrict__ p, double (&c)[N])
+{
+    static_assert(N % 2 == 0, "even");
+#pragma unroll
+    for (int q = 0; q < N; q += 2) {
+        const double2 t = __ldg(reinterpret_cast<const double2 *>(p + q));
+        c[q] = t.x;
+        c[q + 1] = t.y;
+    }
+}
+
+// value of the cell polynomial c[j * (DX+1) + i] at (tx, ty), for two particles at once
+template <int DX, int DY, int NC>
+__device__ __forceinline__ void horner2x2(const double (&c)[NC], double txa, double tya, double txb, double tyb, double &va, double &vb)
+{
+#pragma unroll
+    for (int j = DY; j >= 0; --j) {
+        double ra = c[j * (DX + 1) + DX], rb = ra;
+#pragma unroll
+        for (int i = DX - 1; i >= 0; --i) {
+            ra = fma(ra, txa, c[j * (DX + 1) + i]);
+            rb = fma(rb, txb, c[j * (DX + 1) + i]);
+        }
+        va = (j == DY) ? ra : fma(va, tya, ra);
+        vb = (j == DY) ? rb : fma(vb, tyb, rb);
+    }
+}
+
+template <int D0>
+struct FastParams {
+    Rows2 r;
+    int64_t n, chunk;
+    Mesh2 m;
+    const double *tab;                  // CellTab<D0>::N doubles per cell
+    const double *e[3], *eT[3], *b[3];  // dof arrays (general path)
+    double *j2, *j3;                    // deposit grids (global, zeroed by the launcher)
+    double dtqm_e[2];                   // NHE kick factors (current e, snapshot eT)
+    double dtqm3, wscale3;              // Hp3: dt q/m, charge * common_weight * dt
+    double dt2, qm_h2, wscale_h2;       // Hp2: dt, q/m dy, charge * common_weight * dy
+};
+
+// ---- general per-particle path (any cell, any displacement): global loads and REDs --------------------------
+template <int D0, int NHE, bool HP3, bool HP2>
+__device__ __noinline__ void sorted_general(Part2 &p, const FastParams<D0> &P)
+{
+    constexpr int D1 = D0 - 1;
+    const int nx = P.m.n[0], ny = P.m.n[1];
+    if (NHE > 0 || HP3) {
+        int cx, cy, ix[D0 + 1], iy[D0 + 1];
+        double tx, ty, bx0[D0 + 1], bx1[D1 + 1], by0[D0 + 1], by1[D1 + 1];
+        locate2<0>(p.x[0], P.m, cx, tx);
+        locate2<1>(p.x[1], P.m, cy, ty);
+        stencil<D0>(cx, nx, ix);
+        stencil<D0>(cy, ny, iy);
+        basis_pp<D0>(tx, bx0); basis_pp<D1>(tx, bx1);
+        basis_pp<D0>(ty, by0); basis_pp<D1>(ty, by1);
+        if (NHE > 0) {
+            double k0 = 0.0, k1 = 0.0, k2 = 0.0;
+            for (int h = 0; h < NHE; ++h) {
+                const double *const *f = h == 0 ? P.e : P.eT;
+                k0 = fma(P.dtqm_e[h], eval2<D1, D0, 1, 0, D0>(f[0], nx, ix, iy, bx1, by0), k0);
+                k1 = fma(P.dtqm_e[h], eval2<D0, D1, 0, 1, D0>(f[1], nx, ix, iy, bx0, by1), k1);
+                k2 = fma(P.dtqm_e[h], eval2<D0, D0, 0, 0, D0>(f[2], nx, ix, iy, bx0, by0), k2);
+            }
+            p.v[0] += k0; p.v[1] += k1; p.v[2] += k2;
+        }
+        if (HP3) {
+            const double v3 = p.v[2];
+            const double B1 = eval2<D0, D1, 0, 1, D0>(P.b[0], nx, ix, iy, bx0, by1);
+            const double B2 = eval2<D1, D0, 1, 0, D0>(P.b[1], nx, ix, iy, bx1, by0);
+            p.v[0] = fma(-(P.dtqm3 * v3), B2, p.v[0]);
+            p.v[1] = fma(P.dtqm3 * v3, B1, p.v[1]);
+            const double wv = (p.w * P.wscale3) * v3;
+            for (int b = 0; b <= D0; ++b)
+                for (int a = 0; a <= D0; ++a) atomicAdd(P.j3 + ix[a] + (size_t)iy[b] * nx, (wv * by0[b]) * bx0[a]);
+        }
+    }
+    if (HP2) {
+        P2<Op2Hp12<D0, 1>> Q;
+        Q.m = P.m;
+        Q.f[0] = P.b[2];
+        Q.f[1] = P.b[0];
+        Q.grid = P.j2;
+        const double x_old = p.x[1], x_new = fma(P.dt2, p.v[1], x_old);
+        const typename Op2Hp12<D0, 1>::Sums g = Op2Hp12<D0, 1>::general(x_old, x_new, p.x[0], Q, p.w * P.wscale_h2);
+        p.v[0] = fma(P.qm_h2, g.z, p.v[0]);
+        p.v[2] = fma(-P.qm_h2, g.o, p.v[2]);
+        p.x[1] = pushed<1>(x_old, p.v[1], P.dt2, P.m);
+    }
+}
+
+// registers of one lane that persist across a cell run
+template <int D0, bool HP3, bool HP2>
+struct FastAcc {
+    static constexpr int N3 = HP3 ? (D0 + 1) * (D0 + 1) : 1, N2 = HP2 ? (D0 + 2) * (D0 + 1) : 1;
+    double a3[N3];   // j3[b * (D0+1) + a] at dof (cx-D0+a, cy-D0+b)
+    double a2[N2];   // j2[r * (D0+1) + a] at dof (cx-D0+a, cy-1-D1+r), r = 0 .. D1+2
+};
+
+template <int D0, bool HP3, bool HP2>
+__device__ __forceinline__ void fast_flush(FastAcc<D0, HP3, HP2> &A, int bcx, int bcy, const FastParams<D0> &P, int lane)
+{
+    constexpr int D1 = D0 - 1;
+    const int nx = P.m.n[0], ny = P.m.n[1];
+    if (HP3) {
+#pragma unroll
+        for (int q = 0; q < (D0 + 1) * (D0 + 1); ++q) {
+            double s = A.a3[q];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0 && s != 0.0) {
+                const int b = q / (D0 + 1), a = q - b * (D0 + 1);
+                atomicAdd(P.j3 + wrapi(bcx - D0 + a, nx) + (size_t)wrapi(bcy - D0 + b, ny) * nx, s);
+            }
+            A.a3[q] = 0.0;
+        }
+    }
+    if (HP2) {
+#pragma unroll
+        for (int q = 0; q < (D0 + 2) * (D0 + 1); ++q) {
+            double s = A.a2[q];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0 && s != 0.0) {
+                const int r = q / (D0 + 1), a = q - r * (D0 + 1);
+                atomicAdd(P.j2 + wrapi(bcx - D0 + a, nx) + (size_t)wrapi(bcy - 1 - D1 + r, ny) * nx, s);
+            }
+            A.a2[q] = 0.0;
+        }
+    }
+}
+
+template <int D0, int NHE, bool HP3, bool HP2>
+__global__ void __launch_bounds__(kThreads2, 2) k2_sorted(const __grid_constant__ FastParams<D0> P)
+{
+    using T = CellTab<D0>;
+    constexpr int D1 = D0 - 1, NX0 = D0 + 1, NX1 = D1 + 1, ROWS = D1 + 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nx = P.m.n[0];
+    const int64_t n_chunks = (P.n + P.chunk - 1) / P.chunk;
+    FastAcc<D0, HP3, HP2> A;
+#pragma unroll
+    for (int q = 0; q < A.N3; ++q) A.a3[q] = 0.0;
+#pragma unroll
+    for (int q = 0; q < A.N2; ++q) A.a2[q] = 0.0;
+    for (int64_t ch = (int64_t)blockIdx.x * kWarps2 + warp; ch < n_chunks; ch += (int64_t)gridDim.x * kWarps2) {
+        const int64_t lo = ch * P.chunk, hi = min(P.n, lo + P.chunk);
+        int bcx = -1, bcy = -1;   // cell the register accumulators belong to
+        int64_t i = lo + lane;
+        Part2 a, b;
+        bool ha = i < hi, hb = i + 32 < hi;
+        if (ha) load2<void>(P.r, i, a);
+        if (hb) load2<void>(P.r, i + 32, b);
+        while (__any_sync(0xffffffffu, ha)) {
+            const int64_t ni = i + 64;
+            const bool hc = ni < hi, hd = ni + 32 < hi;
+            Part2 c, d;
+            if (hc) load2<void>(P.r, ni, c);
+            if (hd) load2<void>(P.r, ni + 32, d);
+            // ---- all 64 particles in one cell?
+            int cxa, cya, cxb, cyb;
+            double txa, tya, txb, tyb;
+            locate2<0>(ha ? a.x[0] : 0.0, P.m, cxa, txa);
+            locate2<1>(ha ? a.x[1] : 0.0, P.m, cya, tya);
+            locate2<0>(hb ? b.x[0] : 0.0, P.m, cxb, txb);
+            locate2<1>(hb ? b.x[1] : 0.0, P.m, cyb, tyb);
+            const int kx = __shfl_sync(0xffffffffu, cxa, 0), ky = __shfl_sync(0xffffffffu, cya, 0);
+            const bool inside = (unsigned)kx < (unsigned)nx && (unsigned)ky < (unsigned)P.m.n[1];
+            const bool uni = __all_sync(0xffffffffu, ha && hb && cxa == kx && cxb == kx && cya == ky && cyb == ky) && inside;
+            if (uni) {
+                if (kx != bcx || ky != bcy) {
+                    if (bcx >= 0) fast_flush<D0, HP3, HP2>(A, bcx, bcy, P, lane);
+                    bcx = kx;
+                    bcy = ky;
+                }
+                const double *tab = P.tab + ((size_t)kx + (size_t)ky * nx) * T::N;
+                if (NHE > 0) {
+                    double ka, kb;
+                    {
+                        double c1[T::even(NX1 * NX0)];
+                        ldg_uniform(tab + T::O_E1, c1);
+                        horner2x2<D1, D0>(c1, txa, tya, txb, tyb, ka, kb);
+                        a.v[0] += ka; b.v[0] += kb;
+                    }
+                    {
+                        double c2[T::even(NX0 * NX1)];
+                        ldg_uniform(tab + T::O_E2, c2);
+                        horner2x2<D0, D1>(c2, txa, tya, txb, tyb, ka, kb);
+                        a.v[1] += ka; b.v[1] += kb;
+                    }
+                    {
+                        double c3[T::even(NX0 * NX0)];
+                        ldg_uniform(tab + T::O_E3, c3);
+                        horner2x2<D0, D0>(c3, txa, tya, txb, tyb, ka, kb);
+                        a.v[2] += ka; b.v[2] += kb;
+                    }
+                }
+                double bxa[NX0], bxb[NX0];   // degree-D0 x basis: j3 and j2 deposits, B1 line integral
+                basis_pp<D0>(txa, bxa);
+                basis_pp<D0>(txb, bxb);
+                if (HP3) {
+                    double B1a, B1b, B2a, B2b;
+                    {
+                        double c1[T::even(NX0 * NX1)];
+                        ldg_uniform(tab + T::O_B1, c1);
+                        horner2x2<D0, D1>(c1, txa, tya, txb, tyb, B1a, B1b);
+                    }
+                    {
+                        double c2[T::even(NX1 * NX0)];
+                        ldg_uniform(tab + T::O_B2, c2);
+                        horner2x2<D1, D0>(c2, txa, tya, txb, tyb, B2a, B2b);
+                    }
+                    const double v3a = a.v[2], v3b = b.v[2];
+                    a.v[0] = fma(-(P.dtqm3 * v3a), B2a, a.v[0]);
+                    a.v[1] = fma(P.dtqm3 * v3a, B1a, a.v[1]);
+                    b.v[0] = fma(-(P.dtqm3 * v3b), B2b, b.v[0]);
+                    b.v[1] = fma(P.dtqm3 * v3b, B1b, b.v[1]);
+                    double bya[NX0], byb[NX0];
+                    basis_pp<D0>(tya, bya);
+                    basis_pp<D0>(tyb, byb);
+                    const double wa = (a.w * P.wscale3) * v3a, wb = (b.w * P.wscale3) * v3b;
+#pragma unroll
+                    for (int q = 0; q <= D0; ++q) {
+                        const double ya = wa * bya[q], yb = wb * byb[q];
+#pragma unroll
+                        for (int k = 0; k <= D0; ++k) A.a3[q * NX0 + k] = fma(yb, bxb[k], fma(ya, bxa[k], A.a3[q * NX0 + k]));
+                    }
+                }
+                if (HP2) {
+                    // operatorHp2 (Op2Hp12<D0, 1>::apply) from the common cell (kx, ky)
+                    const double yoa = a.x[1], yob = b.x[1];
+                    const double yna = fma(P.dt2, a.v[1], yoa), ynb = fma(P.dt2, b.v[1], yob);
+                    int cna, cnb;
+                    double tna, tnb;
+                    locate2<1>(yna, P.m, cna, tna);
+                    locate2<1>(ynb, P.m, cnb, tnb);
+                    const int dca = cna - ky, dcb = cnb - ky;
+                    if (__all_sync(0xffffffffu, dca >= -1 && dca <= 1 && dcb >= -1 && dcb <= 1)) {
+                        // window weights of the D1+2 dofs from min(cell_old, cell_new) (see OpStrangFused::work), placed
+                        // in the D1+3 rows cy-1-D1 .. cy+1 a push of at most one cell can reach
+                        double w5a[ROWS], w5b[ROWS];
+                        auto window = [&](double to, double tn, int dc, double (&w5)[ROWS]) {
+                            double Ao[D1 + 1], Bn[D1 + 1], win[D1 + 2];
+                            prim_pp<D1>(to, Ao);
+                            prim_pp<D1>(tn, Bn);
+                            const bool o1 = dc < 0, n1 = dc > 0;
+#pragma unroll
+                            for (int k = 0; k <= D1 + 1; ++k) {
+                                const double F = k <= D1 ? prim_full<D1>(k <= D1 ? k : 0) : 0.0;
+                                const double n0 = k <= D1 ? Bn[k <= D1 ? k : 0] : 0.0, o0 = k <= D1 ? Ao[k <= D1 ? k : 0] : 0.0;
+                                const double nn = k == 0 ? F : (k <= D1 ? F + Bn[k >= 1 ? k - 1 : 0] : Bn[D1]);
+                                const double oo = k == 0 ? F : (k <= D1 ? F + Ao[k >= 1 ? k - 1 : 0] : Ao[D1]);
+                                win[k] = (n1 ? nn : n0) - (o1 ? oo : o0);
+                            }
+                            // the window starts at row 0 when the particle moves down (cmin = cy - 1), at row 1 otherwise
+#pragma unroll
+                            for (int r = 0; r < ROWS; ++r) {
+                                const double lo_ = r <= D1 + 1 ? win[r <= D1 + 1 ? r : 0] : 0.0;
+                                const double hi_ = r >= 1 ? win[r >= 1 ? r - 1 : 0] : 0.0;
+                                w5[r] = o1 ? lo_ : hi_;
+                            }
+                        };
+                        window(tya, tna, dca, w5a);
+                        window(tyb, tnb, dcb, w5b);
+                        double bta[NX1], btb[NX1];   // degree-D1 x basis (B3 is D1 x D1)
+                        basis_pp<D1>(txa, bta);
+                        basis_pp<D1>(txb, btb);
+                        double sza = 0.0, szb = 0.0, soa = 0.0, sob = 0.0;
+                        {
+                            double s3[T::even(ROWS * NX1)];
+                            ldg_uniform(tab + T::O_S3, s3);
+#pragma unroll
+                            for (int r = 0; r < ROWS; ++r) {
+                                double ra = s3[r * NX1] * bta[0], rb = s3[r * NX1] * btb[0];
+#pragma unroll
+                                for (int k = 1; k <= D1; ++k) {
+                                    ra = fma(s3[r * NX1 + k], bta[k], ra);
+                                    rb = fma(s3[r * NX1 + k], btb[k], rb);
+                                }
+                                sza = fma(ra, w5a[r], sza);
+                                szb = fma(rb, w5b[r], szb);
+                            }
+                        }
+                        {
+                            double s1[T::even(ROWS * NX0)];
+                            ldg_uniform(tab + T::O_S1, s1);
+#pragma unroll
+                            for (int r = 0; r < ROWS; ++r) {
+                                double ra = s1[r * NX0] * bxa[0], rb = s1[r * NX0] * bxb[0];
+#pragma unroll
+                                for (int k = 1; k <= D0; ++k) {
+                                    ra = fma(s1[r * NX0 + k], bxa[k], ra);
+                                    rb = fma(s1[r * NX0 + k], bxb[k], rb);
+                                }
+                                soa = fma(ra, w5a[r], soa);
+                                sob = fma(rb, w5b[r], sob);
+                            }
+                        }
+                        const double wqa = a.w * P.wscale_h2, wqb = b.w * P.wscale_h2;
+#pragma unroll
+                        for (int r = 0; r < ROWS; ++r) {
+                            const double ya = wqa * w5a[r], yb = wqb * w5b[r];
+#pragma unroll
+                            for (int k = 0; k <= D0; ++k) A.a2[r * NX0 + k] = fma(yb, bxb[k], fma(ya, bxa[k], A.a2[r * NX0 + k]));
+                        }
+                        a.v[0] = fma(P.qm_h2, sza, a.v[0]);
+                        a.v[2] = fma(-P.qm_h2, soa, a.v[2]);
+                        b.v[0] = fma(P.qm_h2, szb, b.v[0]);
+                        b.v[2] = fma(-P.qm_h2, sob, b.v[2]);
+                        a.x[1] = pushed<1>(yoa, a.v[1], P.dt2, P.m);
+                        b.x[1] = pushed<1>(yob, b.v[1], P.dt2, P.m);
+                    } else {
+                        sorted_general<D0, 0, false, true>(a, P);
+                        sorted_general<D0, 0, false, true>(b, P);
+                    }
+                }
+            } else {
+                if (ha) sorted_general<D0, NHE, HP3, HP2>(a, P);
+                if (hb) sorted_general<D0, NHE, HP3, HP2>(b, P);
+            }
+            if (ha) {
+                if (HP2) P.r.x[1][i] = a.x[1];
+                P.r.v[0][i] = a.v[0];
+                P.r.v[1][i] = a.v[1];
+                if (NHE > 0 || HP2) P.r.v[2][i] = a.v[2];
+            }
+            if (hb) {
+                if (HP2) P.r.x[1][i + 32] = b.x[1];
+                P.r.v[0][i + 32] = b.v[0];
+                P.r.v[1][i + 32] = b.v[1];
+                if (NHE > 0 || HP2) P.r.v[2][i + 32] = b.v[2];
+            }
+            a = c; b = d;
+            ha = hc; hb = hd;
+            i = ni;
+        }
+        if (bcx >= 0) fast_flush<D0, HP3, HP2>(A, bcx, bcy, P, lane);
+    }
+}
+
 // sum_p w v.v, sum_p w v_k: one block-reduced partial per block, finished by k_reduce_partials
 __global__ void __launch_bounds__(256) k2_moments(Rows2 r, int64_t n, double *__restrict__ partials)
 {
@@ -1037,6 +1476,90 @@ static void fused_he_hp3(Splitting2D &h, double dt, int n_he, double dt_T)
     m2d_e_from_j(*h.maxwell, h.e(2), h.j(2), 3);
 }
 
+// ---- sorted fast path: host side ---------------------------------------------------------------------------
+template <int D0>
+static void build_celltab(Splitting2D &h, int nhe, double dtqm_e0, double dtqm_e1)
+{
+    using T = CellTab<D0>;
+    const size_t need = h.nd * (size_t)T::N;
+    if (h.celltab.n < need) h.celltab.alloc(need);
+    CellTabParams P{};
+    for (int c = 0; c < 3; ++c) { P.e[c] = h.e(c); P.eT[c] = h.eT(c); P.b[c] = h.b(c); }
+    P.dtqm_e[0] = dtqm_e0; P.dtqm_e[1] = dtqm_e1;
+    P.nx = h.maxwell->nx; P.ny = h.maxwell->ny; P.nhe = nhe;
+    P.out = h.celltab.p;
+    k2_build_celltab<D0><<<(int)((h.nd + 127) / 128), 128, 0, ctx().stream>>>(P);
+    GP_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+template <int D0, int NHE, bool HP3, bool HP2>
+static void launch_sorted(Splitting2D &h, FastParams<D0> P, const char *tag)
+{
+    Context &c = ctx();
+    P.r = rows2(*h.pg);
+    P.n = h.pg->n;
+    P.m = mesh2(*h.maxwell);
+    P.tab = h.celltab.p;
+    for (int k = 0; k < 3; ++k) { P.e[k] = h.e(k); P.eT[k] = h.eT(k); P.b[k] = h.b(k); }
+    P.j2 = h.j(1);
+    P.j3 = h.j(2);
+    if (P.n <= 0) return;
+    int per_sm = 0;
+    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_sorted<D0, NHE, HP3, HP2>, kThreads2, 0));
+    GP_REQUIRE(per_sm >= 1, GEMPIC_EINVAL, "sorted pass does not fit on an SM");
+    const int64_t warps = (int64_t)c.sm_count * per_sm * kWarps2;
+    int64_t chunk = (P.n + warps * 16 - 1) / (warps * 16);
+    chunk = std::max<int64_t>(512, std::min<int64_t>((chunk + 63) / 64 * 64, 16384));
+    P.chunk = chunk;
+    const int64_t n_chunks = (P.n + chunk - 1) / chunk;
+    const int grid = (int)std::min<int64_t>((n_chunks + kWarps2 - 1) / kWarps2, (int64_t)c.sm_count * per_sm);
+    if (tag) profile_begin(tag);
+    k2_sorted<D0, NHE, HP3, HP2><<<grid, kThreads2, 0, c.stream>>>(P);
+    GP_CUDA(cudaGetLastError());
+    if (tag) profile_end(tag);
+    count_launch();
+}
+
+// head of a Strang step from the cell-sorted order: [HE x n_he, Hp3, Hp2](dt/2) in one register-resident pass + the
+// e3 and e2 solves (nothing between them reads e)
+static void sorted_head(Splitting2D &h, double dt, int n_he, double dt_T)
+{
+    const double qm = h.pg->q_over_m, cq = h.pg->charge * h.pg->common_weight;
+    GP_CUDA(cudaMemsetAsync(h.j(1), 0, 2 * h.nd * sizeof(double), ctx().stream));   // j2 | j3 adjacent
+    GP_DISPATCH_D0(h.maxwell->s_deg_0, {
+        build_celltab<D0>(h, n_he, 0.5 * dt * qm, 0.5 * dt_T * qm);
+        FastParams<D0> P{};
+        P.dtqm_e[0] = 0.5 * dt * qm;
+        P.dtqm_e[1] = 0.5 * dt_T * qm;
+        P.dtqm3 = 0.5 * dt * qm;
+        P.wscale3 = cq * 0.5 * dt;
+        P.dt2 = 0.5 * dt;
+        P.qm_h2 = qm * h.maxwell->dy;
+        P.wscale_h2 = cq * h.maxwell->dy;
+        if (n_he == 1) launch_sorted<D0, 1, true, true>(h, P, "fused[HE,Hp3,Hp2]{2,3}");
+        else launch_sorted<D0, 2, true, true>(h, P, "fused[HE,HE,Hp3,Hp2]{2,3}");
+    });
+    h.pg->sorted2d = false;
+    allreduce_sum(h.j(1), 2 * h.nd);
+    m2d_e_from_j(*h.maxwell, h.e(2), h.j(2), 3);
+    m2d_e_from_j(*h.maxwell, h.e(1), h.j(1), 2);
+}
+
+// tail of a Strang step: Hp3(dt/2) right after the sorting Hp2 (same b, so the table of sorted_head is still valid)
+static void sorted_hp3(Splitting2D &h, double dt)
+{
+    zero_grid(h.j(2), h.nd);
+    GP_DISPATCH_D0(h.maxwell->s_deg_0, {
+        FastParams<D0> P{};
+        P.dtqm3 = dt * h.pg->q_over_m;
+        P.wscale3 = h.pg->charge * h.pg->common_weight * dt;
+        launch_sorted<D0, 0, true, false>(h, P, "operatorHp3{2,3} sorted");
+    });
+    allreduce_sum(h.j(2), h.nd);
+    m2d_e_from_j(*h.maxwell, h.e(2), h.j(2), 3);
+}
+
 // strang_splitting! with the point-wise operators fused (same trajectory up to rounding):
 //   first step      HB ; [b -= dt/2 curl e] ; fused{HE,Hp3} ; Hp2 Hp1 Hp2 Hp3
 //   between steps   eT = e ; b -= dt/2 curl e ; HB ; HB ; b -= dt/2 curl e ; fused{HE(eT),HE,Hp3} ; Hp2 Hp1 Hp2 Hp3
@@ -1050,6 +1573,8 @@ static void strang2d_fused(Splitting2D &h, double dt, int64_t steps)
     // sort_interval == 1: the cell sort rides in the last push of every step (sorting_hp2); a stand-alone sort is only
     // needed when somebody else has moved the particles since
     const bool ride = h.sort_interval == 1 && h.pg->W == 1 && h.pg->n >= 2;
+    // fuse level 2: the operators that start from the sorted order run on the register-resident fast path (k2_sorted)
+    const bool fast = ride && h.fuse >= 2;
     // a trailing HE kick this splitting left pending in its previous call (fields already advanced, snapshot in eT)
     // rides in the first pass of this one; anybody else's is applied first
     ParticleGroup &pg = *h.pg;
@@ -1065,20 +1590,23 @@ static void strang2d_fused(Splitting2D &h, double dt, int64_t steps)
         if (s == 0) {
             hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);
             m2d_b_from_e(m, b, 0.5 * dt, e);
-            fused_he_hp3(h, dt, pending ? 2 : 1, pending ? h.pending_dt : dt);
+            if (fast) sorted_head(h, dt, pending ? 2 : 1, pending ? h.pending_dt : dt);
+            else fused_he_hp3(h, dt, pending ? 2 : 1, pending ? h.pending_dt : dt);
         } else {
             GP_CUDA(cudaMemcpyAsync(h.eT(0), h.e(0), 3 * h.nd * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
             m2d_b_from_e(m, b, 0.5 * dt, e);              // trailing HE of step s-1, field part
             hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);     // trailing HB of step s-1
             hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);     // leading HB of step s
             m2d_b_from_e(m, b, 0.5 * dt, e);              // leading HE of step s, field part
-            fused_he_hp3(h, dt, 2, dt);
+            if (fast) sorted_head(h, dt, 2, dt);
+            else fused_he_hp3(h, dt, 2, dt);
         }
-        hs2d_operator(h, GEMPIC_OP_HP2, 0.5 * dt);
+        if (!fast) hs2d_operator(h, GEMPIC_OP_HP2, 0.5 * dt);
         hs2d_operator(h, GEMPIC_OP_HP1, dt);
         if (ride) sorting_hp2(h, 0.5 * dt);
         else hs2d_operator(h, GEMPIC_OP_HP2, 0.5 * dt);
-        hs2d_operator(h, GEMPIC_OP_HP3, 0.5 * dt);
+        if (fast) sorted_hp3(h, 0.5 * dt);
+        else hs2d_operator(h, GEMPIC_OP_HP3, 0.5 * dt);
         h.steps_done++;
     }
     // trailing HE + HB: the fields are advanced now; the particle kick, which only reads the snapshot eT, is deferred to
@@ -1259,11 +1787,14 @@ int gempic_hs2d_set_sort_interval(gempic_handle hs, int interval)
     GP_API_END
 }
 
-/* 1 (default): fused particle passes inside strang_splitting ([HE,Hp3] and the cross-step HE fold); 0: one pass per operator */
+/* 2 (default): fused particle passes inside strang_splitting, the operators that start from the cell-sorted order on
+ * the register-resident fast path (k2_sorted); 1: fused [HE,Hp3] tile pass and the cross-step HE fold only;
+ * 0: one pass per operator */
 int gempic_hs2d_set_fusion(gempic_handle hs, int fuse)
 {
     GP_API_BEGIN
-    get<Splitting2D>(hs, "HamiltonianSplitting{2,3}")->fuse = fuse ? 1 : 0;
+    GP_REQUIRE(fuse >= 0 && fuse <= 2, GEMPIC_EINVAL, "fuse must be 0, 1 or 2");
+    get<Splitting2D>(hs, "HamiltonianSplitting{2,3}")->fuse = fuse;
     GP_API_END
 }
 

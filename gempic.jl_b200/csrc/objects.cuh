@@ -201,7 +201,8 @@ struct Splitting2D : Object {
     ParticleGroup *pg = nullptr;
     size_t nd = 0;             // nx * ny
     DevBuf<double> fields;     // e1 e2 e3 b1 b2 b3 j1 j2 j3 rho e1T e2T e3T (13 * nd) + 16 scalars
-    int fuse = 1;              // fused [HE,Hp3] pass and cross-step HE fold inside strang_splitting
+    int fuse = 2;              // 2: + sorted fast path (k2_sorted), 1: fused [HE,Hp3] pass and cross-step HE fold, 0: per operator
+    DevBuf<double> celltab;    // per-cell field tables of the sorted fast path (hs2d.cu CellTab)
     PartialScratch scratch;
     int sort_interval = 1;     // cell-sort every k Strang steps (0: never)
     int64_t steps_done = 0;

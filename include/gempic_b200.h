@@ -251,7 +251,8 @@ int gempic_hs2d_strang_splitting_host(gempic_handle hs, double dt, int64_t numbe
                                       double *e3, double *b1, double *b2, double *b3);
 /* cell-sort the particles every `interval` Strang steps (0: never; default 1) */
 int gempic_hs2d_set_sort_interval(gempic_handle hs, int interval);
-/* 1 (default): fused [HE,Hp3] pass and cross-step HE fold inside strang_splitting; 0: one pass per operator */
+/* 2 (default): fused passes inside strang_splitting, the operators that start from the cell-sorted order on the
+ * register-resident fast path; 1: fused [HE,Hp3] tile pass and cross-step HE fold only; 0: one pass per operator */
 int gempic_hs2d_set_fusion(gempic_handle hs, int fuse);
 /* add_charge! of all particles onto the degree p x p dofs (get_charge weights), summed over ranks */
 int gempic_hs2d_charge_density(gempic_handle hs, double *rho);
