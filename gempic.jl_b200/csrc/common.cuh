@@ -42,6 +42,7 @@ struct Context {
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
+    uint64_t particle_epoch = 1;   // bumped by every launch that writes particle rows (invalidates ParticleGroup::tail)
     // multi-GPU
     void *nccl_comm = nullptr;
     int n_ranks = 1, rank = 0;
@@ -52,6 +53,7 @@ struct Context {
 Context &ctx();
 void require_init();
 inline void count_launch(int n = 1) { ctx().launches += n; }
+inline void particles_changed() { ctx().particle_epoch++; }
 // optional per-kernel device timing (CUDA events around each tagged launch, no host sync);
 // read back with gempic_profile_read after a synchronize
 void profile_begin(const char *tag);

@@ -1291,6 +1291,7 @@ static void launch2(Splitting2D &h, P2<Op> P, const char *tag)
     GP_CUDA(cudaGetLastError());
     if (tag) profile_end(tag);
     count_launch();
+    if (Op::WRITE_X || Op::WRITE_V) particles_changed();
 }
 
 #define GP_DISPATCH_D0(Dv, ...)                                                           \
@@ -1519,6 +1520,7 @@ static void launch_sorted(Splitting2D &h, FastParams<D0> P, const char *tag)
     GP_CUDA(cudaGetLastError());
     if (tag) profile_end(tag);
     count_launch();
+    particles_changed();
 }
 
 // head of a Strang step from the cell-sorted order: [HE x n_he, Hp3, Hp2](dt/2) in one register-resident pass + the

@@ -108,6 +108,7 @@ inline void launch_pass(PassParams<Op> P, PartialScratch *scratch, double *out, 
     GP_CUDA(cudaGetLastError());
     if (tag) profile_end(tag);
     count_launch();
+    if (Op::WRITE != 0) particles_changed();
     if (Op::DEPOSIT && defer) {
         defer->partials = P.partials;
         defer->n_blocks = grid;

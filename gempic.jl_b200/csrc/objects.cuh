@@ -23,6 +23,17 @@ struct ParticleGroup : Object {
     size_t stride = 0;    // row pitch in doubles (multiple of 32 -> 256 B aligned rows)
     DevBuf<double> sort_tmp;
     DevBuf<int> sort_keys;    // per-cell counters / cursors of the 2D sort
+    // Results of the loop-tail pass (hs1d.cu loop_tail_pass, OpLoopTail): this rank's rho deposit and write_step! sums,
+    // valid while no launch has written particle rows since (Context::particle_epoch) and the caller asks with the same
+    // smoothers / fields.  gempic_solve_poisson and gempic_diag_write_step look here before running their own pass.
+    struct TailCache {
+        uint64_t epoch = 0;
+        bool rho_valid = false, diag_valid = false;
+        double key[12] = {0};          // degree, n, xmin, dx, scaling of both smoothers, Lx of the solver
+        DevBuf<double> buf;            // [rho (n) | KE, P1, P2, transfer, vvb]
+        std::vector<double> fields;    // host copy of e1 | e2 | b the sums were taken with
+    } tail;
+    bool exposed = false;     // a raw row pointer was handed out (gempic_pg_row_ptr): writes can no longer be tracked
     uint64_t generation = 0;  // bumped whenever the row pointers change (sort)
     bool sorted2d = false;    // rows are in 2D cell order (hs2d.cu keeps them so); cleared by whoever rewrites positions
     ParticleGroup() : Object(kKind) {}
@@ -164,6 +175,10 @@ struct Splitting : Object {
     // particles (hs1d.cu).  j2_stale implies ParticleGroup::pending == this.
     bool j2_stale = false;
     bool j2_unreduced = false;     // j2() holds this rank's share only; summed by hs_materialise_j2 (collective)
+    // e1 | e2 | b as last delivered to the host (gempic_hs_get_fields) and the field epoch they belong to: lets the
+    // loop-tail pass know that the caller's arrays are the fields it is about to take the write_step! sums with
+    std::vector<double> stash;
+    uint64_t stash_epoch = 0, fields_epoch = 1;
     double j2_scale = 0.0;
     Splitting() : Object(kKind) {}
     ~Splitting() override;   // drops a pending kick registration and releases maxwell, ks0, ks1, pg (hs1d.cu)
@@ -233,6 +248,7 @@ inline ParticleGroup *get_pg(gempic_handle h)
 void hs_operator(Splitting &h, int op, double dt, bool inside_strang);
 void hs_strang(Splitting &h, double dt, int64_t steps);
 void hs_materialise_j2(Splitting &h);
+void tail_key(const Pmc1D &ks0, const Pmc1D &ks1, double Lmod, double (&key)[12]);
 void boris_push_v_epart(Boris &s, double dt);
 void boris_push_v_bpart(Boris &s, double dt);
 void boris_push_x_accumulate_j(Boris &s, double dt);

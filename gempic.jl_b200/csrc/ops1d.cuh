@@ -746,6 +746,46 @@ struct OpHEJ2 {
     }
 };
 
+// ---- the particle part of a diagnostics loop body after a fused strang_splitting! in ONE pass (48 B/particle):
+//      examples/strong_landau_damping_1d2v.jl:46-59 calls strang_splitting!; solve_poisson!; write_step! every step.
+//      The deferred trailing operatorHE kick (with the j_dofs[2] deposit that must precede it, OpHEJ2), the rho deposit
+//      of solve_poisson! (diagnostics.jl:24-28) and the five particle sums of write_step! (:45-92,197-211, taken with
+//      the kicked velocities) read the same rows.  fields: [e1T, e2T (kick), e1, e2, b (sums)]; grids: j2, rho;
+//      scalars: KE, P1, P2, transfer, vvb.
+template <int D0, int D1>
+struct OpLoopTail {
+    static constexpr int READ = ROW_X | ROW_V1 | ROW_V2 | ROW_W, WRITE = ROW_V1 | ROW_V2;
+    static constexpr int NF = 5, NG = 2, NS = 5;
+    static constexpr bool DEPOSIT = true;
+    struct Params { double dtqm, wscale0, charge, mass, cw; };
+    template <bool LP>
+    static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpLoopTail> &P, const double *sf, const Acc<LP> &acc)
+    {
+        const int nh = P.m.n + kHalo;
+        const Pos ps = locate(p.x, P.m);
+        int g0, g1;
+        first_dofs<D0, D1>(ps, P.m, g0, g1);
+        double b1[D1 + 1], b0[D0 + 1];
+        basis_pp<D1>(ps.t, b1);
+        basis_pp<D0>(ps.t, b0);
+        const double ws = p.w * P.op.wscale0;
+        deposit_h<D0, LP>(acc, g0, b0, ws * p.v2);                       // j_dofs[2] before the kick (OpHEJ2)
+        kick_e<D0, D1>(p, g0, g1, b0, b1, sf, sf + nh, P.op.dtqm);
+        deposit_h<D0, LP>(acc, nh + g0, b0, ws);                          // add_charge! (OpCharge)
+        double wm = p.w * P.op.mass;                                      // OpDiag, operation for operation
+        wm *= P.op.cw;
+        acc.add(2 * nh + 0, (p.v1 * p.v1 + p.v2 * p.v2) * wm);
+        acc.add(2 * nh + 1, p.v1 * wm);
+        acc.add(2 * nh + 2, p.v2 * wm);
+        const double e1 = gather_h<D1>(sf + 2 * nh, g1, b1);
+        const double e2 = gather_h<D0>(sf + 3 * nh, g0, b0);
+        const double bf = gather_h<D1>(sf + 4 * nh, g1, b1);
+        const double wq = P.op.charge * p.w * P.op.cw;
+        acc.add(2 * nh + 3, (p.v1 * e1 + p.v2 * e2) * wq);
+        acc.add(2 * nh + 4, wq * p.v1 * p.v2 * bf);
+    }
+};
+
 // ---- 1d1v operatorHB = E-kick without q/m (hamiltonian_splitting_1d1v.jl:113-125). fields: [e1]
 template <int D1>
 struct OpHB11 {

@@ -46,6 +46,7 @@ static const int64_t kStageParticles = 1 << 22;  // 4 Mi records per staging chu
 
 void pg_upload(ParticleGroup &pg, const double *aos)
 {
+    particles_changed();
     Context &c = ctx();
     pg.sorted2d = false;
     const int rows = pg.rows();
@@ -205,6 +206,7 @@ void sort_scan(int *counts, int64_t total)
 
 void pg_sort_1d(ParticleGroup &pg, const Pmc1D &p)
 {
+    particles_changed();
     pg.sorted2d = false;
     Context &c = ctx();
     if (pg.n < 2) return;
@@ -311,6 +313,7 @@ __global__ void __launch_bounds__(256) k_sort2_scatter(const double *__restrict_
 
 void pg_sort_2d(ParticleGroup &pg, const Maxwell2D &mx)
 {
+    particles_changed();
     Context &c = ctx();
     if (pg.n < 2) return;
     GP_REQUIRE(pg.D == 2, GEMPIC_EINVAL, "2D cell sort needs a D = 2 particle group");
@@ -415,6 +418,7 @@ __global__ void k_sample(double *__restrict__ data, size_t stride, int D, int V,
 void pg_sample(ParticleGroup &pg, int kind, double xmin, double L, double alpha, double k, const double *sigma,
                uint64_t seed, int64_t first_index)
 {
+    particles_changed();
     Context &c = ctx();
     pg.sorted2d = false;
     GP_REQUIRE(kind == 0 || kind == 1, GEMPIC_EINVAL, "unknown sample kind %d", kind);

@@ -185,6 +185,7 @@ int gempic_pg_sample_landau(gempic_handle h, double alpha, double k, double sigm
                (long long)first_index, (long long)(first_index + pg->n), (long long)n_global);
     GP_REQUIRE(n_global < ((int64_t)1 << kSobolBits), GEMPIC_EINVAL, "the Sobol sequence of Sobol.jl has 2^32 - 1 points");
     pg->sorted2d = false;
+    particles_changed();
     if (pg->n == 0) return GEMPIC_OK;
     static const SobolTable T = make_sobol_table();
     LandauParams s{alpha, k, sigma, weight, first_index, n_global};
@@ -224,6 +225,7 @@ int gempic_pg_sample_cos_gaussian(gempic_handle h, int sampling_type, int symmet
     }
     GP_REQUIRE(cum == 1.0, GEMPIC_EASSERT, "sum(delta) == 1.0 (distributions.jl:44)");
     pg->sorted2d = false;
+    particles_changed();
     if (pg->n == 0) return GEMPIC_OK;
     static const SobolTable T = make_sobol_table();
     k_sample_cos_gauss<<<ctx().sm_count * 8, 256, 0, ctx().stream>>>(pg->data.p, pg->stride, pg->n, s, T);

@@ -150,6 +150,61 @@ def test_deferred_trailing_kick_is_invisible(orc, gp):
     assert rel_err(e1c, e1b) < 1e-10 and rel_err(sg.e1, so.e1) < 1e-10 and rel_err(sg.b, so.b) < 1e-10
 
 
+def test_loop_tail_results_are_only_reused_when_valid(orc, gp):
+    """after a fused strang_splitting! the pass that applies the deferred kick also deposits rho and takes the
+    write_step! sums (OpLoopTail, csrc/hs1d.cu loop_tail_pass); solve_poisson! / write_step! reuse them only while
+    nothing has written the particles and the caller passes the fields that call delivered.  Every variant must equal
+    the oracle: hit, other fields (miss), particles replaced (miss), a second smoother degree for rho (miss)."""
+    n = 40_000
+    state = weibel_state(n, L_WEIBEL, seed=41)
+    so, sg = both(orc, gp, state, L_WEIBEL, nx=32)
+    so.init_fields(b_amp=1e-2, e2_amp=1e-3), sg.init_fields(b_amp=1e-2, e2_amp=1e-3)
+    ho, hg = so.splitting(), sg.splitting()
+    th = gp.TimeHistoryDiagnostics(sg.pg, sg.mx, sg.ks0, sg.ks1)
+    epo, epg, rho_o, rho_g = np.zeros(32), np.zeros(32), np.zeros(32), np.zeros(32)
+
+    def diag(fields_o, fields_g, b_o, b_g):
+        ref = orc.write_step(so.pg, so.mx, so.ks0, so.ks1, 0.1, 3, fields_o, b_o, fields_o, epo)
+        got = gp.write_step(th, 0.1, 3, fields_g, b_g, fields_g, epg)
+        ke = abs(ref[1])
+        for k in range(1, 11):
+            assert abs(got[k] - ref[k]) < 1e-10 * max(abs(ref[k]), 1e-6 * ke), gp.DIAG_COLUMNS[k]
+
+    for it in range(3):
+        ho.strang_splitting(0.05, 1), hg.strang_splitting(0.05, 1)
+        launches = gp.launch_count(reset=True)
+        orc.solve_poisson(epo, so.pg, so.ks0, so.mx, rho_o)
+        gp.solve_poisson(epg, sg.pg, sg.ks0, sg.mx, rho_g)                      # applies the kick: loop-tail pass
+        assert rel_err(rho_g, rho_o) < TOL and rel_err(epg, epo) < 1e-11
+        diag([so.e1, so.e2], [sg.e1, sg.e2], so.b, sg.b)                         # hit
+        if it == 0:
+            used = gp.launch_count()
+        # other fields than the step delivered: the sums must be taken again
+        diag([so.e1 * 1.5, so.e2 + 1e-3], [sg.e1 * 1.5, sg.e2 + 1e-3], so.b * 0.5, sg.b * 0.5)
+        diag([so.e1, so.e2], [sg.e1, sg.e2], so.b, sg.b)                         # and the hit still works
+    # the hit path of one loop body: loop tail + its reduction, the Poisson solve, five field kernels of write_step!
+    # -- and NO second or third particle pass (OpCharge, OpDiag each add a pass + a reduction)
+    assert used <= 12, used
+    # rho on another smoother: miss
+    rho2o, rho2g, e2o, e2g = np.zeros(32), np.zeros(32), np.zeros(32), np.zeros(32)
+    ho.strang_splitting(0.05, 1), hg.strang_splitting(0.05, 1)
+    orc.solve_poisson(e2o, so.pg, so.ks1, so.mx, rho2o)
+    gp.solve_poisson(e2g, sg.pg, sg.ks1, sg.mx, rho2g)
+    assert rel_err(rho2g, rho2o) < TOL
+    # particles replaced after the tail pass: miss for both
+    ho.strang_splitting(0.05, 1), hg.strang_splitting(0.05, 1)
+    orc.solve_poisson(epo, so.pg, so.ks0, so.mx, rho_o)
+    gp.solve_poisson(epg, sg.pg, sg.ks0, sg.mx, rho_g)
+    st2 = so.particles().copy()
+    st2[1] *= 1.25
+    so.pg.array[:, :] = st2
+    sg.pg.upload(st2)
+    orc.solve_poisson(epo, so.pg, so.ks0, so.mx, rho_o)
+    gp.solve_poisson(epg, sg.pg, sg.ks0, sg.mx, rho_g)
+    assert rel_err(rho_g, rho_o) < TOL
+    diag([so.e1, so.e2], [sg.e1, sg.e2], so.b, sg.b)
+
+
 def test_fused_j_dofs_rebuilt_on_demand(orc, gp):
     """the fused pass adds both Hp2 half-step currents into one grid (their two e2 solves are linear); `j_dofs` as the
     reference leaves it -- zero j1, dt/2 * j2 of the SECOND Hp2 -- is rebuilt from the particles when it is looked at:
