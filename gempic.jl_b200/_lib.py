@@ -88,6 +88,23 @@ def init(device: int | None = None):
     _initialised = True
 
 
+def init_devices(devices):
+    """ONE process driving several devices (gempic_init_devices): `devices` is a list of CUDA device ids or a count.
+    Afterwards every object is replicated / sharded over them inside the library; the Python API is unchanged
+    (ParticleGroup takes the global particle count)."""
+    global _initialised
+    if _initialised:
+        raise GempicError(1, "the library is already initialised")
+    ids = list(range(devices)) if isinstance(devices, int) else [int(d) for d in devices]
+    arr = (C.c_int * len(ids))(*ids)
+    check(load().gempic_init_devices(C.c_int(len(ids)), arr))
+    _initialised = True
+
+
+def device_count() -> int:
+    return int(load().gempic_device_count())
+
+
 def finalize():
     global _initialised
     if _initialised:

@@ -168,6 +168,7 @@ int gempic_pmc1d_destroy(gempic_handle pmc)
 static void accumulate_host(double *host, const double *dev_new, int n, double *dev_old_tmp)
 {
     // host[i] += dev_new[i], evaluated on the device in fp64 (x + y is exact IEEE either way)
+    if (!host_out_enabled()) return;   // in-process multi-device run: rank 0 alone touches the caller's array
     h2d(dev_old_tmp, host, n);
     field_axpby(dev_old_tmp, 1.0, dev_new, 1.0, n);
     d2h(host, dev_old_tmp, n);
@@ -484,9 +485,14 @@ int gempic_hs_get_fields(gempic_handle hs, double *e1, double *e2, double *b, do
     d2h_vectors(dst, h->fields.p, 5, h->n);   // e1 | e2 | b | j1 | j2 are adjacent
     if (e1 && e2 && b) {   // remember what the caller now holds (loop_tail_pass, hs1d.cu)
         h->stash.resize((size_t)3 * h->n);
-        std::memcpy(h->stash.data(), e1, sizeof(double) * h->n);
-        std::memcpy(h->stash.data() + h->n, e2, sizeof(double) * h->n);
-        std::memcpy(h->stash.data() + 2 * (size_t)h->n, b, sizeof(double) * h->n);
+        if (host_out_enabled()) {
+            std::memcpy(h->stash.data(), e1, sizeof(double) * h->n);
+            std::memcpy(h->stash.data() + h->n, e2, sizeof(double) * h->n);
+            std::memcpy(h->stash.data() + 2 * (size_t)h->n, b, sizeof(double) * h->n);
+        } else {   // rank > 0 of an in-process multi-device run: rank 0 is writing the caller's arrays right now
+            GP_CUDA(cudaMemcpyAsync(h->stash.data(), h->fields.p, sizeof(double) * 3 * h->n, cudaMemcpyDeviceToHost, ctx().stream));
+            GP_CUDA(cudaStreamSynchronize(ctx().stream));
+        }
         h->stash_epoch = h->fields_epoch;
     }
     GP_API_END
@@ -667,7 +673,7 @@ int gempic_solve_poisson(gempic_handle pgh, gempic_handle pmc0, gempic_handle mh
     }
     allreduce_sum(drho, p->n_grid);
     field_e_from_rho(*m, de, drho);
-    if (rho) GP_CUDA(cudaMemcpyAsync(rho, drho, sizeof(double) * m->n, cudaMemcpyDeviceToHost, ctx().stream));
+    if (rho && host_out_enabled()) GP_CUDA(cudaMemcpyAsync(rho, drho, sizeof(double) * m->n, cudaMemcpyDeviceToHost, ctx().stream));
     d2h(efield, de, m->n);
     GP_API_END
 }
@@ -718,6 +724,7 @@ int gempic_diag_write_step(gempic_handle pgh, gempic_handle mh, gempic_handle pm
     field_max_abs_diff(d_e1, d_ep, n, d_out + 9);
     double r[10];
     d2h(r, d_out, 10);
+    if (!host_out_enabled()) return GEMPIC_OK;
     out11[0] = time;
     out11[1] = r[0]; out11[2] = r[1]; out11[3] = r[2];
     out11[4] = r[6]; out11[5] = r[7]; out11[6] = r[8];

@@ -9,7 +9,12 @@
 #include <unordered_map>
 #include <vector>
 
+#include <functional>
+
 #include "../../include/gempic_b200.h"
+#ifndef GEMPIC_NO_RENAME
+#include "md_rename.inc"   // gempic_X -> gempic_impl_X: the .cu files define the per-rank implementations (md.cu wraps them)
+#endif
 
 namespace gempic {
 
@@ -50,8 +55,12 @@ struct Context {
     double *pinned = nullptr;  // small pinned staging buffer for field I/O
     size_t pinned_bytes = 0;
 };
-Context &ctx();
+Context &ctx();   // of the calling thread's rank (one per process, or one per device after gempic_init_devices)
 void require_init();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (rank, kernel, size): function attributes are per device
+void ensure_func_smem(const void *func, size_t bytes);
+// false on the ranks > 0 of an in-process multi-device run: replicated host outputs are written by rank 0 only
+bool host_out_enabled();
 inline void count_launch(int n = 1) { ctx().launches += n; }
 inline void particles_changed() { ctx().particle_epoch++; }
 // optional per-kernel device timing (CUDA events around each tagged launch, no host sync);
@@ -60,6 +69,19 @@ void profile_begin(const char *tag);
 void profile_end(const char *tag);
 // sum-allreduce `n` doubles in place on the library stream (no-op for one rank)
 void allreduce_sum(double *dev, int64_t n);
+
+// ---- in-process multi-device mode (gempic_init_devices; runtime.cu, md.cu) --------------------------------------
+namespace md {
+bool dispatching();   // multi-device mode is on and the caller is not one of the worker threads
+int n_ranks();
+// fn(rank) on every worker thread / on rank 0's thread / on the calling thread with rank 0's state (C callbacks);
+// returns the first non-zero status and leaves that rank's message in the caller's gempic_last_error()
+int run_all(const std::function<int(int)> &fn);
+int run_rank0(const std::function<int(int)> &fn);
+int run_on_caller(const std::function<int(int)> &fn);
+void shard(int64_t n_global, int rank, int64_t &first, int64_t &count);   // index range of a rank (multiples of 32)
+void set_host_out(bool on);   // calling worker: write host outputs (per-particle arrays) although it is not rank 0
+}  // namespace md
 
 // ---- device buffers -------------------------------------------------------------------
 template <typename T>

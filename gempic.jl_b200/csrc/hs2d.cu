@@ -1011,7 +1011,7 @@ __device__ __forceinline__ void fast_flush(FastAcc<D0, HP3, HP2> &A, int bcx, in
 }
 
 template <int D0, int NHE, bool HP3, bool HP2>
-__global__ void __launch_bounds__(kThreads2, 2) k2_sorted(const __grid_constant__ FastParams<D0> P)
+__global__ void __launch_bounds__(kThreads2, HP2 ? 2 : 3) k2_sorted(const __grid_constant__ FastParams<D0> P)
 {
     using T = CellTab<D0>;
     constexpr int D1 = D0 - 1, NX0 = D0 + 1, NX1 = D1 + 1, ROWS = D1 + 3;
@@ -1271,11 +1271,7 @@ static void launch2(Splitting2D &h, P2<Op> P, const char *tag)
     P.m = mesh2(*h.maxwell);
     if (P.n <= 0) return;
     const size_t smem = (size_t)kWarps2 * warp_smem_doubles<Op>() * sizeof(double);
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
-        GP_CUDA(cudaFuncSetAttribute(k2_pass<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    if (smem > 48 * 1024) ensure_func_smem((const void *)k2_pass<Op>, smem);
     int per_sm = 0;
     GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_pass<Op>, kThreads2, smem));
     GP_REQUIRE(per_sm >= 1, GEMPIC_EINVAL, "2D pass does not fit on an SM (smem %zu B)", smem);
@@ -1392,12 +1388,9 @@ static void sorting_hp2(Splitting2D &h, double dt)
     int *hist = pg.sort_keys.p;
     GP_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * cells, c.stream));
     const Mesh2 m = mesh2(*h.maxwell);
-    static bool configured = false;
     const size_t hsmem = (size_t)cells * sizeof(int);
-    if (!configured && hsmem > 48 * 1024) {
-        GP_CUDA(cudaFuncSetAttribute(k2_hist_after_hp2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
-        configured = true;
-    }
+    GP_REQUIRE(hsmem <= kSmemMaxOptin, GEMPIC_EINVAL, "riding sort: %d cells exceed the shared-memory histogram", cells);
+    if (hsmem > 48 * 1024) ensure_func_smem((const void *)k2_hist_after_hp2, hsmem);
     profile_begin("cell histogram after Hp2");
     const int hgrid = (int)std::min<int64_t>((int64_t)c.sm_count * 8, (pg.n + 255) / 256);
     k2_hist_after_hp2<<<hgrid, 256, hsmem, c.stream>>>(rows2(pg), pg.n, dt, m, cells, hist);
@@ -1733,7 +1726,7 @@ int gempic_hs2d_get_fields(gempic_handle hs, double *e1, double *e2, double *e3,
     Splitting2D *h = get<Splitting2D>(hs, "HamiltonianSplitting{2,3}");
     double *dst[9] = {e1, e2, e3, b1, b2, b3, j1, j2, j3};
     for (int k = 0; k < 9; ++k)
-        if (dst[k])
+        if (dst[k] && host_out_enabled())
             GP_CUDA(cudaMemcpyAsync(dst[k], h->fields.p + k * h->nd, h->nd * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
     GP_CUDA(cudaStreamSynchronize(ctx().stream));
     GP_API_END

@@ -62,11 +62,7 @@ template <class Op, bool LP>
 inline int configure_kernel(size_t smem)
 {
     auto kern = k_pass<Op, LP>;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        GP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (smem > 48 * 1024) ensure_func_smem((const void *)kern, smem);
     int per_sm = 0;
     GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, op_threads<Op>::value, smem));
     return per_sm;

@@ -332,11 +332,9 @@ void pg_sort_2d(ParticleGroup &pg, const Maxwell2D &mx)
     if (pg.sort_keys.n < need) pg.sort_keys.alloc(need);
     if (pg.sort_tmp.n < pg.data.n) pg.sort_tmp.alloc(pg.data.n);
     int *hist = pg.sort_keys.p, *blockhist = pg.sort_keys.p + cells;
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
-        GP_CUDA(cudaFuncSetAttribute(k_sort2_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        GP_CUDA(cudaFuncSetAttribute(k_sort2_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
+    if (smem > 48 * 1024) {
+        ensure_func_smem((const void *)k_sort2_hist, 200 * 1024);
+        ensure_func_smem((const void *)k_sort2_scatter, 200 * 1024);
     }
     GP_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * cells, c.stream));
     profile_begin("cell sort 2d");

@@ -5,8 +5,10 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <condition_variable>
 #include <cstdarg>
 #include <cstring>
+#include <thread>
 
 #include "common.cuh"
 
@@ -35,18 +37,62 @@ void fail(int code, const char *fmt, ...)
     throw Fail{code};
 }
 
-static Context g_ctx;
+// ---- ranks ------------------------------------------------------------------------------
+// All mutable library state lives in a Rank: the context (device, stream, communicator), the handle registry, the
+// pinned staging cursor and the profiling slots.  A process normally has ONE rank (gempic_init).  After
+// gempic_init_devices(n, ids) it has n, one per device, each driven by its own worker thread (md.cu); every API call
+// is then executed by all of them -- the in-process form of "one process per GPU".  `t_rank` is the rank the calling
+// thread works for.
+struct ProfSlot {
+    std::string tag;
+    double ms = 0.0;
+    int64_t launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+struct Rank {
+    Context ctx;
+    std::mutex mu;
+    std::unordered_map<gempic_handle, std::unique_ptr<Object>> objects;
+    std::vector<std::unique_ptr<Object>> zombies;   // destroyed handles that a splitting object still points to
+    gempic_handle next = 0x1000;
+    size_t pinned_off = 0;
+    bool profile = false;
+    std::vector<ProfSlot> prof;
+    std::vector<cudaEvent_t> event_pool;
+    std::unordered_map<const void *, size_t> func_smem;
+    bool host_out = true;
+};
+static Rank g_rank0;
+static thread_local Rank *t_rank = &g_rank0;
+static Rank &rk() { return *t_rank; }
+#define g_ctx (rk().ctx)
+#define g_mu (rk().mu)
+#define g_objects (rk().objects)
+#define g_next (rk().next)
+#define g_zombies (rk().zombies)
+#define g_pinned_off (rk().pinned_off)
+#define g_profile (rk().profile)
+#define g_prof (rk().prof)
+#define g_event_pool (rk().event_pool)
+
 Context &ctx() { return g_ctx; }
+bool host_out_enabled() { return rk().host_out; }
 
 void require_init()
 {
     GP_REQUIRE(g_ctx.ready, GEMPIC_ENOTINIT, "gempic_init() has not been called (or no CUDA device)");
 }
 
+void ensure_func_smem(const void *func, size_t bytes)
+{
+    size_t &have = rk().func_smem[func];
+    if (bytes > have) {
+        GP_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
+}
+
 // ---- registry -------------------------------------------------------------------------
-static std::mutex g_mu;
-static std::unordered_map<gempic_handle, std::unique_ptr<Object>> g_objects;
-static gempic_handle g_next = 0x1000;
 
 gempic_handle register_object(std::unique_ptr<Object> obj)
 {
@@ -64,8 +110,6 @@ Object *lookup(gempic_handle h, Kind kind, const char *what)
         fail(GEMPIC_EHANDLE, "invalid %s handle 0x%llx", what, (unsigned long long)h);
     return it->second.get();
 }
-
-static std::vector<std::unique_ptr<Object>> g_zombies;   // destroyed handles that a splitting object still points to
 
 void retain(Object *o)
 {
@@ -134,7 +178,6 @@ void destroy_all()
 // Small host vectors (field dofs) go through a pinned bump buffer so that H2D copies are
 // truly asynchronous and the caller's buffer can be reused as soon as the call returns.
 static const size_t kPinnedBytes = 1 << 20;
-static size_t g_pinned_off = 0;
 
 static void ensure_pinned()
 {
@@ -202,6 +245,10 @@ void d2h_vectors(double *const *host, const double *dev, int k, size_t n)
         GP_CUDA(cudaStreamSynchronize(c.stream));
         return;
     }
+    if (!host_out_enabled()) {   // replicated result: rank 0 writes the caller's arrays
+        GP_CUDA(cudaStreamSynchronize(c.stream));
+        return;
+    }
     const size_t bytes = (size_t)(last + 1) * n * sizeof(double);
     if (bytes > kPinnedBytes / 4) {
         for (int i = 0; i <= last; ++i)
@@ -226,22 +273,12 @@ void d2h_vectors(double *const *host, const double *dev, int k, size_t n)
 void d2h(double *host, const double *dev, size_t n)
 {
     Context &c = ctx();
-    GP_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    if (host_out_enabled()) GP_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     GP_CUDA(cudaStreamSynchronize(c.stream));
     g_pinned_off = 0;
 }
 
 // ---- per-kernel profiling ---------------------------------------------------------------
-struct ProfSlot {
-    std::string tag;
-    double ms = 0.0;
-    int64_t launches = 0;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
-};
-static bool g_profile = false;
-static std::vector<ProfSlot> g_prof;
-static std::vector<cudaEvent_t> g_event_pool;
-
 static cudaEvent_t take_event()
 {
     if (!g_event_pool.empty()) {
@@ -296,15 +333,18 @@ struct NcclApi {
     void *lib = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
 
+static std::mutex g_nccl_mu;
 static NcclApi &nccl()
 {
-    if (g_nccl.lib) return g_nccl;
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.lib && g_nccl.GetErrorString) return g_nccl;
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char *nm : names) {
         g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
@@ -316,6 +356,7 @@ static NcclApi &nccl()
     GP_REQUIRE(g_nccl.field, GEMPIC_ENCCL, "libnccl lacks %s", name)
     GP_SYM(GetUniqueId, "ncclGetUniqueId");
     GP_SYM(CommInitRank, "ncclCommInitRank");
+    GP_SYM(CommInitAll, "ncclCommInitAll");
     GP_SYM(CommDestroy, "ncclCommDestroy");
     GP_SYM(AllReduce, "ncclAllReduce");
     GP_SYM(GetErrorString, "ncclGetErrorString");
@@ -338,14 +379,187 @@ void allreduce_sum(double *dev, int64_t n)
     count_launch();
 }
 
+// ---- in-process multi-device mode ----------------------------------------------------------------------------
+namespace md {
+
+struct Worker {
+    Rank rank;
+    int device = 0, index = 0;
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    const std::function<int(int)> *job = nullptr;
+    bool done = true, quit = false;
+    int rc = 0;
+    std::string err;
+};
+static std::vector<std::unique_ptr<Worker>> g_workers;
+static thread_local bool t_in_worker = false;
+
+static void worker_main(Worker *w)
+{
+    cudaSetDevice(w->device);
+    t_rank = &w->rank;
+    t_in_worker = true;
+    std::unique_lock<std::mutex> lk(w->m);
+    for (;;) {
+        w->cv.wait(lk, [&] { return w->job || w->quit; });
+        if (w->quit) return;
+        const std::function<int(int)> *job = w->job;
+        lk.unlock();
+        int rc;
+        try {
+            rc = (*job)(w->index);
+        } catch (...) {
+            set_error("internal error in the worker of device %d", w->device);
+            rc = GEMPIC_ECUDA;
+        }
+        lk.lock();
+        w->rc = rc;
+        w->err = rc ? g_error : std::string();
+        w->job = nullptr;
+        w->done = true;
+        w->cv.notify_all();
+    }
+}
+
+bool dispatching() { return !g_workers.empty() && !t_in_worker; }
+int n_ranks() { return g_workers.empty() ? 1 : (int)g_workers.size(); }
+
+static int run_on(const std::function<int(int)> &fn, int first, int last)
+{
+    for (int r = first; r < last; ++r) {
+        Worker &w = *g_workers[r];
+        std::lock_guard<std::mutex> lk(w.m);
+        w.job = &fn;
+        w.done = false;
+        w.cv.notify_all();
+    }
+    int rc = 0;
+    for (int r = first; r < last; ++r) {
+        Worker &w = *g_workers[r];
+        std::unique_lock<std::mutex> lk(w.m);
+        w.cv.wait(lk, [&] { return w.done; });
+        if (w.rc && !rc) {
+            rc = w.rc;
+            g_error = w.err;
+        }
+    }
+    return rc;
+}
+int run_all(const std::function<int(int)> &fn) { return run_on(fn, 0, (int)g_workers.size()); }
+int run_rank0(const std::function<int(int)> &fn) { return run_on(fn, 0, 1); }
+int run_on_caller(const std::function<int(int)> &fn)
+{
+    // the workers are idle between dispatches, so the caller may borrow rank 0's state (host-only work: the set-up
+    // quadratures that call back into the caller's language run here, never on a foreign thread)
+    Rank *saved = t_rank;
+    t_rank = &g_workers[0]->rank;
+    int rc;
+    try {
+        rc = fn(0);
+    } catch (...) {
+        t_rank = saved;
+        throw;
+    }
+    t_rank = saved;
+    return rc;
+}
+
+void shard(int64_t n_global, int rank, int64_t &first, int64_t &count)
+{
+    const int64_t R = n_ranks();
+    int64_t per = (n_global + R - 1) / R;
+    per = (per + 31) / 32 * 32;   // multiples of 32: symmetric sampling needs multiples of 8, rows stay 256 B aligned
+    first = std::min<int64_t>((int64_t)rank * per, n_global);
+    count = std::min<int64_t>(per, n_global - first);
+}
+
+void set_host_out(bool on) { rk().host_out = on; }
+
+static void stop_workers()
+{
+    for (auto &w : g_workers) {
+        {
+            std::lock_guard<std::mutex> lk(w->m);
+            w->quit = true;
+            w->cv.notify_all();
+        }
+        if (w->th.joinable()) w->th.join();
+    }
+    g_workers.clear();
+}
+
+}  // namespace md
 }  // namespace gempic
 
 using namespace gempic;
 
+static int init_this_rank(int device);
+
 extern "C" {
+
+int gempic_device_count(void) { return md::n_ranks(); }
+
+int gempic_init_devices(int n_devices, const int *device_ids)
+{
+    GP_API_BEGIN
+    GP_REQUIRE(!g_rank0.ctx.ready && md::g_workers.empty(), GEMPIC_EINVAL, "the library is already initialised");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        fail(GEMPIC_ENOTINIT, "no CUDA device available (%s); libgempic_b200 has no CPU path",
+             e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    GP_REQUIRE(n_devices >= 1 && n_devices <= count, GEMPIC_EINVAL, "%d devices requested, %d visible", n_devices, count);
+    std::vector<int> ids(n_devices);
+    for (int r = 0; r < n_devices; ++r) {
+        ids[r] = device_ids ? device_ids[r] : r;
+        GP_REQUIRE(ids[r] >= 0 && ids[r] < count, GEMPIC_EINVAL, "device %d out of range [0,%d)", ids[r], count);
+        for (int q = 0; q < r; ++q) GP_REQUIRE(ids[q] != ids[r], GEMPIC_EINVAL, "device %d listed twice", ids[r]);
+    }
+    for (int r = 0; r < n_devices; ++r) {
+        auto w = std::make_unique<md::Worker>();
+        w->device = ids[r];
+        w->index = r;
+        w->rank.host_out = r == 0;
+        w->th = std::thread(md::worker_main, w.get());
+        md::g_workers.push_back(std::move(w));
+    }
+    int rc = md::run_all([&](int r) { return init_this_rank(ids[r]); });
+    if (rc == GEMPIC_OK && n_devices > 1) {
+        std::vector<ncclComm_t> comms(n_devices);
+        ncclResult_t nr = nccl().CommInitAll(comms.data(), n_devices, ids.data());
+        if (nr != ncclSuccess) {
+            set_error("ncclCommInitAll failed: %s", nccl().GetErrorString(nr));
+            rc = GEMPIC_ENCCL;
+        } else {
+            for (int r = 0; r < n_devices; ++r) {
+                Context &c = md::g_workers[r]->rank.ctx;
+                c.nccl_comm = comms[r];
+                c.n_ranks = n_devices;
+                c.rank = r;
+            }
+        }
+    }
+    if (rc != GEMPIC_OK) {
+        md::run_all([&](int) { return gempic_finalize(); });   // (renamed: the per-rank implementation)
+        md::stop_workers();
+        return rc;
+    }
+    GP_API_END
+}
 
 const char *gempic_last_error(void) { return g_error.c_str(); }
 int gempic_version(void) { return 100; }
+
+}  // extern "C"
+
+static int init_this_rank(int device) { return gempic_init(device); }
+
+// called by md.cu after the workers have finalised their ranks
+namespace gempic { namespace md { void shutdown() { stop_workers(); } } }
+
+extern "C" {
 
 int gempic_init(int device)
 {

@@ -15,7 +15,8 @@
  *   - host pointers are borrowed for the duration of the call only.
  *   - particle arrays cross the boundary in the reference layout: column-major
  *     (D+V+n_weights) x N  (src/particle_group.jl:29), i.e. one record per particle.
- *   - one device per process (gempic_init); calls on one handle are not re-entrant.
+ *   - one device per process (gempic_init) or n devices driven by one process (gempic_init_devices); calls are
+ *     synchronous and not re-entrant.
  */
 #ifndef GEMPIC_B200_H
 #define GEMPIC_B200_H
@@ -53,6 +54,16 @@ const char *gempic_last_error(void);
 int gempic_version(void);
 /* Bind the process to CUDA device `device` and create the library stream. */
 int gempic_init(int device);
+/* ONE host process driving n devices (the reference chunks its particles over threads inside one process,
+ * src/hamiltonian_splitting.jl:61-66): after this call every entry point below acts on all n devices -- objects are
+ * replicated, particle groups are sharded by index range (gempic_pg_create takes the GLOBAL particle count; upload /
+ * download / sample address the global array), deposits are all-reduced over NCCL (ncclCommInitAll), replicated host
+ * outputs are written once.  Each device is driven by its own worker thread inside the library; calls stay synchronous
+ * for the caller.  device_ids == NULL: devices 0 .. n-1.  Not combinable with gempic_init / gempic_comm_init; raw
+ * device-pointer entry points (gempic_pg_row_ptr, gempic_pg_set/get_row_device) are refused in this mode. */
+int gempic_init_devices(int n_devices, const int *device_ids);
+/* number of ranks this process drives: 1 after gempic_init, n after gempic_init_devices(n, ..) */
+int gempic_device_count(void);
 int gempic_finalize(void);
 int gempic_synchronize(void);
 /* cudaStream_t the library launches on (for CUDA-event timing by the caller). */

@@ -27,3 +27,47 @@ def test_sharded_equals_unsharded(tmp_path, nproc):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = json.load(open(out))
     assert res["ok"], res
+
+
+@pytest.mark.parametrize("n_dev", [2, 4, 8])
+def test_one_process_drives_all_devices(tmp_path, n_dev):
+    """gempic_init_devices: ONE host process, n devices, unchanged API (global particle counts, global arrays).  The same
+    script (tests/md_worker.py: device samplers, fused 1d2v steps with the diagnostics loop, Boris, 2d3v with the riding
+    sort) runs on 1 and on n devices; everything a caller can observe must agree."""
+    import os
+    import subprocess
+    import sys
+
+    import numpy as np
+
+    if _n_gpus() < n_dev:
+        pytest.skip(f"needs {n_dev} GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for n in (1, n_dev):
+        outs[n] = str(tmp_path / f"md{n}.npz")
+        r = subprocess.run([sys.executable, os.path.join(root, "tests", "md_worker.py"), str(n), outs[n]], cwd=root,
+                           capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    a, b = np.load(outs[1]), np.load(outs[n_dev])
+    assert set(a.files) == set(b.files)
+    for k in a.files:
+        x, y = a[k], b[k]
+        assert x.shape == y.shape, k
+        if k in ("landau_load", "sym_load", "error"):
+            assert np.array_equal(x, y), k                 # the loads depend on the global index only
+            continue
+        if k == "diag":                                    # momenta / transfer terms cancel to ~0: scale by the energy
+            scale = np.maximum(np.abs(x), 1e-9 * np.max(np.abs(x[:, 1])))
+            assert np.max(np.abs(x - y) / scale) < 1e-9, k
+            continue
+        if k.endswith("particles"):
+            L = 4 * np.pi
+            d = np.abs(x - y)
+            nx = 2 if k.startswith("hs2d") else 1
+            d[:nx] = np.minimum(d[:nx], np.abs(d[:nx] - L))
+            assert np.max(d) < 1e-10 * L, k
+            continue
+        for row_x, row_y in zip(np.atleast_2d(x), np.atleast_2d(y)):
+            s = np.max(np.abs(row_x))
+            assert np.max(np.abs(row_x - row_y)) <= 1e-11 * max(s, 1e-300) or s == 0.0, k
