@@ -84,6 +84,7 @@ static void boris_fields(Boris &s, bool post, bool pre, double dt, const Deferre
     BorisFields F{};
     F.n_partials = defer ? defer->n_blocks : -1;
     F.partials = defer ? defer->partials : nullptr;
+    F.x = defer ? xchg_next() : XchgDev{};
     F.e1 = s.f(GEMPIC_F_E1); F.e2 = s.f(GEMPIC_F_E2); F.b = s.f(GEMPIC_F_B);
     F.j1 = s.f(GEMPIC_F_J1); F.j2 = s.f(GEMPIC_F_J2);
     F.e1_mid = s.f(GEMPIC_F_E1_MID); F.e2_mid = s.f(GEMPIC_F_E2_MID); F.b_mid = s.f(GEMPIC_F_B_MID);
@@ -130,7 +131,7 @@ void boris_strang(Boris &s, double dt, int64_t steps)
     if (steps <= 0) return;
     boris_fields(s, false, true, dt);
     // one GPU: the per-block partial sums of the pass are reduced by the field kernel itself (one launch less)
-    const bool single = ctx().n_ranks == 1;
+    const bool single = ctx().n_ranks == 1 || xchg_active();   // several GPUs: summed over the ranks in the same kernel (xchg.cuh)
     for (int64_t i = 0; i < steps; ++i) {
         DeferredReduce dr, *defer = single ? &dr : nullptr;
         boris_particles(s, dt, defer);

@@ -12,6 +12,7 @@
 #include <functional>
 
 #include "../../include/gempic_b200.h"
+#include "xchg.cuh"
 #ifndef GEMPIC_NO_RENAME
 #include "md_rename.inc"   // gempic_X -> gempic_impl_X: the .cu files define the per-rank implementations (md.cu wraps them)
 #endif
@@ -52,6 +53,10 @@ struct Context {
     void *nccl_comm = nullptr;
     int n_ranks = 1, rank = 0;
     int suspended_ranks = 0;   // gempic_comm_suspend: n_ranks while this rank works on its own
+    // NVLink peer-memory exchange (xchg.cuh): buffers of all ranks as mapped here; ready once every rank has them
+    bool xchg_ready = false;
+    double *xchg_buf[kXchgMaxRanks] = {nullptr};
+    unsigned long long xchg_seq = 0;
     double *pinned = nullptr;  // small pinned staging buffer for field I/O
     size_t pinned_bytes = 0;
 };
@@ -67,8 +72,12 @@ inline void particles_changed() { ctx().particle_epoch++; }
 // read back with gempic_profile_read after a synchronize
 void profile_begin(const char *tag);
 void profile_end(const char *tag);
-// sum-allreduce `n` doubles in place on the library stream (no-op for one rank)
+// sum-allreduce `n` doubles in place on the library stream (no-op for one rank): one k_xchg_allreduce launch over peer
+// memory when the exchange buffers are mapped and the vector fits, ncclAllReduce otherwise
 void allreduce_sum(double *dev, int64_t n);
+// descriptor of the NEXT in-kernel exchange (advances the sequence number); n_ranks = 1 when there is nothing to exchange
+XchgDev xchg_next();
+inline bool xchg_active() { return ctx().xchg_ready && ctx().n_ranks > 1; }
 
 // ---- in-process multi-device mode (gempic_init_devices; runtime.cu, md.cu) --------------------------------------
 namespace md {

@@ -127,6 +127,10 @@ __global__ void k_strang_fields(StrangFields F)
             for (int q = 0; q < groups; ++q) sum += red[q * F.n_acc + g];
             acc[g] = sum;
         }
+        if (F.x.n_ranks > 1) {   // sum over the ranks through peer memory (rank order: identical on every rank)
+            __syncthreads();
+            xchg_allreduce_block(F.x, acc, F.n_acc, 0, 0);
+        }
     } else if (F.do_solve) {
         for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) acc[i] = F.acc[i];
     }
@@ -266,6 +270,7 @@ __global__ void k_boris_fields(BorisFields F)
             F.j1[g] = sum;   // j1 | j2 are adjacent
         }
         __syncthreads();
+        if (F.x.n_ranks > 1) xchg_allreduce_block(F.x, F.j1, n_acc, 0, 0);
     }
     if (F.do_post) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) {

@@ -148,6 +148,7 @@ static void strang_fields(Splitting &h, bool solve, double dt, bool tail, double
     StrangFields F{};
     F.n_partials = defer ? defer->n_blocks : -1;
     F.partials = defer ? defer->partials : nullptr;
+    F.x = defer ? xchg_next() : XchgDev{};
     F.n_acc = 2 * h.n;
     F.e1 = h.e1(); F.e2 = h.e2(); F.b = h.b(); F.j1 = h.j1(); F.acc = h.acc(); F.eT = h.e1T();   // e1T | e2T adjacent
     F.do_solve = solve; F.j2_scale = 0.5 * dt;
@@ -275,8 +276,10 @@ static void strang_fused(Splitting &h, double dt, int64_t steps)
     const bool pending = pg.pending != nullptr;
     pg.pending = nullptr;
     strang_fields(h, false, dt, false, dt, true, dt);
-    // one GPU: the per-block partial sums of the pass are reduced by the field kernel itself (one launch less)
-    const bool single = ctx().n_ranks == 1;
+    // the per-block partial sums of the pass are reduced by the field kernel itself -- and, on several GPUs with mapped
+    // exchange buffers, summed over the ranks in the same launch (xchg.cuh): pass + field kernel = 2 launches per step;
+    // without the buffers: k_reduce_partials, ncclAllReduce, field kernel
+    const bool single = ctx().n_ranks == 1 || xchg_active();
     for (int64_t s = 0; s < steps; ++s) {
         DeferredReduce dr, *defer = single ? &dr : nullptr;
         if (s == 0) fused_pass(h, dt, pending ? 2 : 1, pending ? h.pending_dt : dt, defer);

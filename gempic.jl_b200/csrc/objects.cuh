@@ -107,6 +107,7 @@ struct StrangFields {
     // already reduced -- and all-reduced -- by the caller)
     const double *partials;
     int n_partials, n_acc;
+    XchgDev x;   // several ranks, n_partials >= 0: the locally reduced acc is summed over the ranks inside the kernel (xchg.cuh)
 };
 void field_strang_fields(const Maxwell1D &m, StrangFields F);
 // the same for HamiltonianSplittingBoris: step (4) of the step just pushed and step (1) of the next one
@@ -120,6 +121,7 @@ struct BorisFields {
     // single GPU: per-block partial sums [j1 | j2] of the pass, reduced into j1, j2 by this kernel (n_partials < 0: done)
     const double *partials;
     int n_partials;
+    XchgDev x;   // like StrangFields::x
 };
 void field_boris_fields(const Maxwell1D &m, BorisFields F);
 void field_b_from_e(const Maxwell1D &m, double *b, double dt, const double *e);

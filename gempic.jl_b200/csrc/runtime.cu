@@ -6,7 +6,9 @@
 #include <nccl.h>
 
 #include <condition_variable>
+#include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -77,6 +79,7 @@ static Rank &rk() { return *t_rank; }
 
 Context &ctx() { return g_ctx; }
 bool host_out_enabled() { return rk().host_out; }
+namespace md { static bool g_in_process_peers = false; }   // exchange buffers are plain peer pointers (gempic_init_devices)
 
 void require_init()
 {
@@ -336,6 +339,7 @@ struct NcclApi {
     ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -359,6 +363,7 @@ static NcclApi &nccl()
     GP_SYM(CommInitAll, "ncclCommInitAll");
     GP_SYM(CommDestroy, "ncclCommDestroy");
     GP_SYM(AllReduce, "ncclAllReduce");
+    GP_SYM(AllGather, "ncclAllGather");
     GP_SYM(GetErrorString, "ncclGetErrorString");
 #undef GP_SYM
     return g_nccl;
@@ -371,12 +376,115 @@ static NcclApi &nccl()
             ::gempic::fail(GEMPIC_ENCCL, "%s failed: %s", #expr, nccl().GetErrorString(_r)); \
     } while (0)
 
+// ---- peer-memory exchange (xchg.cuh) -------------------------------------------------------------------------
+// stand-alone form: block b owns a slice of the vector and flag b
+__global__ void __launch_bounds__(256) k_xchg_allreduce(XchgDev X, double *__restrict__ v, int n, int per_block)
+{
+    const int lo = blockIdx.x * per_block;
+    const int cnt = min(per_block, n - lo);
+    if (cnt > 0) xchg_allreduce_block(X, v + lo, cnt, blockIdx.x, lo);
+}
+
+XchgDev xchg_next()
+{
+    Context &c = ctx();
+    XchgDev X{};
+    X.n_ranks = 1;
+    if (!c.xchg_ready || c.n_ranks <= 1) return X;
+    X.n_ranks = c.n_ranks;
+    X.rank = c.rank;
+    X.seq = ++c.xchg_seq;
+    for (int r = 0; r < c.n_ranks; ++r) X.buf[r] = c.xchg_buf[r];
+    return X;
+}
+
 void allreduce_sum(double *dev, int64_t n)
 {
     Context &c = ctx();
     if (c.n_ranks <= 1 || n <= 0) return;
+    if (c.xchg_ready && n <= kXchgSlot) {
+        int blocks = (int)std::min<int64_t>(kXchgFlags, (n + 511) / 512);
+        const int per_block = (int)((n + blocks - 1) / blocks);
+        blocks = (int)((n + per_block - 1) / per_block);
+        k_xchg_allreduce<<<blocks, 256, 0, c.stream>>>(xchg_next(), dev, (int)n, per_block);
+        GP_CUDA(cudaGetLastError());
+        count_launch();
+        return;
+    }
     GP_NCCL(nccl().AllReduce(dev, dev, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)c.nccl_comm, c.stream));
     count_launch();
+}
+
+static bool xchg_wanted()
+{
+    const char *e = getenv("GEMPIC_NO_XCHG");
+    return !(e && e[0] && e[0] != '0');
+}
+
+// every rank agrees (min over ranks) on whether the exchange buffers are usable; a single rank that failed to map a
+// peer would otherwise wait for exchanges the others route through NCCL
+static void xchg_agree(bool mine_ok)
+{
+    Context &c = ctx();
+    DevBuf<double> flag(1);
+    const double v = mine_ok ? 0.0 : 1.0;
+    GP_CUDA(cudaMemcpyAsync(flag.p, &v, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    GP_NCCL(nccl().AllReduce(flag.p, flag.p, 1, ncclDouble, ncclSum, (ncclComm_t)c.nccl_comm, c.stream));
+    double sum = 1.0;
+    GP_CUDA(cudaMemcpyAsync(&sum, flag.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    GP_CUDA(cudaStreamSynchronize(c.stream));
+    c.xchg_ready = sum == 0.0;
+}
+
+// one process per GPU: allocate the buffer, all-gather the cudaIpc handles through NCCL, map the peers
+static void xchg_setup_ipc()
+{
+    Context &c = ctx();
+    c.xchg_ready = false;
+    if (c.n_ranks <= 1 || c.n_ranks > kXchgMaxRanks || !c.nccl_comm) return;
+    bool ok = xchg_wanted();
+    double *mine = nullptr;
+    cudaIpcMemHandle_t hmine;
+    std::memset(&hmine, 0, sizeof(hmine));
+    if (ok) ok = cudaMalloc(&mine, kXchgBufDoubles * sizeof(double)) == cudaSuccess;
+    if (ok) ok = cudaMemset(mine, 0, kXchgBufDoubles * sizeof(double)) == cudaSuccess;
+    if (ok) ok = cudaIpcGetMemHandle(&hmine, mine) == cudaSuccess;
+    cudaGetLastError();
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    DevBuf<double> send(8), recv((size_t)8 * c.n_ranks);
+    GP_CUDA(cudaMemcpyAsync(send.p, &hmine, 64, cudaMemcpyHostToDevice, c.stream));
+    GP_NCCL(nccl().AllGather(send.p, recv.p, 8, ncclDouble, (ncclComm_t)c.nccl_comm, c.stream));
+    std::vector<cudaIpcMemHandle_t> all(c.n_ranks);
+    GP_CUDA(cudaMemcpyAsync(all.data(), recv.p, (size_t)64 * c.n_ranks, cudaMemcpyDeviceToHost, c.stream));
+    GP_CUDA(cudaStreamSynchronize(c.stream));
+    xchg_agree(ok);              // everybody has a buffer and a handle?
+    if (!c.xchg_ready) {
+        if (mine) cudaFree(mine);
+        return;
+    }
+    c.xchg_buf[c.rank] = mine;
+    for (int r = 0; r < c.n_ranks && ok; ++r) {
+        if (r == c.rank) continue;
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = false;
+        c.xchg_buf[r] = (double *)p;
+    }
+    cudaGetLastError();
+    xchg_agree(ok);              // everybody has mapped everybody?
+    c.xchg_seq = 0;
+}
+
+static void xchg_teardown()
+{
+    Context &c = ctx();
+    for (int r = 0; r < kXchgMaxRanks; ++r) {
+        if (!c.xchg_buf[r]) continue;
+        if (r == c.rank) cudaFree(c.xchg_buf[r]);
+        else if (!md::g_in_process_peers) cudaIpcCloseMemHandle(c.xchg_buf[r]);
+        c.xchg_buf[r] = nullptr;
+    }
+    c.xchg_ready = false;
+    cudaGetLastError();
 }
 
 // ---- in-process multi-device mode ----------------------------------------------------------------------------
@@ -539,6 +647,42 @@ int gempic_init_devices(int n_devices, const int *device_ids)
                 c.n_ranks = n_devices;
                 c.rank = r;
             }
+            // exchange buffers over plain peer access (same process: no IPC handles needed)
+            if (n_devices <= kXchgMaxRanks && xchg_wanted()) {
+                std::vector<double *> bufs(n_devices, nullptr);
+                std::vector<int> okv(n_devices, 0);
+                md::run_all([&](int r) {
+                    bool ok = true;
+                    for (int q = 0; q < n_devices && ok; ++q) {
+                        if (q == r) continue;
+                        int can = 0;
+                        ok = cudaDeviceCanAccessPeer(&can, ids[r], ids[q]) == cudaSuccess && can;
+                        if (ok) {
+                            const cudaError_t pe = cudaDeviceEnablePeerAccess(ids[q], 0);
+                            ok = pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled;
+                        }
+                    }
+                    cudaGetLastError();
+                    if (ok) ok = cudaMalloc(&bufs[r], kXchgBufDoubles * sizeof(double)) == cudaSuccess &&
+                                 cudaMemset(bufs[r], 0, kXchgBufDoubles * sizeof(double)) == cudaSuccess;
+                    cudaDeviceSynchronize();
+                    okv[r] = ok ? 1 : 0;
+                    return 0;
+                });
+                bool all_ok = true;
+                for (int r = 0; r < n_devices; ++r) all_ok = all_ok && okv[r];
+                md::g_in_process_peers = true;
+                for (int r = 0; r < n_devices; ++r) {
+                    Context &c = md::g_workers[r]->rank.ctx;
+                    if (all_ok) {
+                        for (int q = 0; q < n_devices; ++q) c.xchg_buf[q] = bufs[q];
+                        c.xchg_ready = true;
+                        c.xchg_seq = 0;
+                    } else {
+                        c.xchg_buf[r] = bufs[r];   // freed by xchg_teardown
+                    }
+                }
+            }
         }
     }
     if (rc != GEMPIC_OK) {
@@ -594,6 +738,7 @@ int gempic_finalize(void)
     cudaStreamSynchronize(c.stream);
     destroy_all();
     if (c.nccl_comm) {
+        xchg_teardown();
         nccl().CommDestroy((ncclComm_t)c.nccl_comm);
         c.nccl_comm = nullptr;
         c.n_ranks = 1;
@@ -704,6 +849,7 @@ int gempic_comm_init(int n_ranks, int rank, const void *id128)
     c.nccl_comm = comm;
     c.n_ranks = n_ranks;
     c.rank = rank;
+    xchg_setup_ipc();
     GP_API_END
 }
 
@@ -713,6 +859,7 @@ int gempic_comm_finalize(void)
     Context &c = ctx();
     if (c.nccl_comm) {
         cudaStreamSynchronize(c.stream);
+        xchg_teardown();
         GP_NCCL(nccl().CommDestroy((ncclComm_t)c.nccl_comm));
         c.nccl_comm = nullptr;
     }
