@@ -27,6 +27,7 @@
 //     same stencil: broadcast, conflict free); outside the window a particle reads global memory;
 //   * the next two particles of every lane are loaded before the current two are processed.
 #include <algorithm>
+#include <cstdlib>
 
 #include "hostutil.hpp"
 #include "objects.cuh"
@@ -914,15 +915,22 @@ struct FastParams {
     const double *tab;                  // CellTab<D0>::N doubles per cell
     const double *e[3], *eT[3], *b[3];  // dof arrays (general path)
     double *j2, *j3;                    // deposit grids (global, zeroed by the launcher)
-    double dtqm_e[2];                   // NHE kick factors (current e, snapshot eT)
+    double dtqm_e[2];                   // kick factors (current e, snapshot eT)
+    int nhe;                            // number of electric kicks folded into the table (general path: 1 or 2)
     double dtqm3, wscale3;              // Hp3: dt q/m, charge * common_weight * dt
     double dt2, qm_h2, wscale_h2;       // Hp2: dt, q/m dy, charge * common_weight * dy
 };
 
 // ---- general per-particle path (any cell, any displacement): global loads and REDs --------------------------
+// Out of line and BY VALUE: a by-reference particle would pin the particles of the fast path to local memory (ncu r2e:
+// 47 % of the stall samples of the Hp3 pass sat on the STL that parked a freshly loaded row on the stack).
+struct SortedOut { double x1, v0, v1, v2; };
 template <int D0, int NHE, bool HP3, bool HP2>
-__device__ __noinline__ void sorted_general(Part2 &p, const FastParams<D0> &P)
+__device__ __noinline__ SortedOut sorted_general_v(double px0, double px1, double pv0, double pv1, double pv2, double pw,
+                                                   const FastParams<D0> &P)
 {
+    Part2 p;
+    p.x[0] = px0; p.x[1] = px1; p.v[0] = pv0; p.v[1] = pv1; p.v[2] = pv2; p.w = pw;
     constexpr int D1 = D0 - 1;
     const int nx = P.m.n[0], ny = P.m.n[1];
     if (NHE > 0 || HP3) {
@@ -936,7 +944,7 @@ __device__ __noinline__ void sorted_general(Part2 &p, const FastParams<D0> &P)
         basis_pp<D0>(ty, by0); basis_pp<D1>(ty, by1);
         if (NHE > 0) {
             double k0 = 0.0, k1 = 0.0, k2 = 0.0;
-            for (int h = 0; h < NHE; ++h) {
+            for (int h = 0; h < P.nhe; ++h) {
                 const double *const *f = h == 0 ? P.e : P.eT;
                 k0 = fma(P.dtqm_e[h], eval2<D1, D0, 1, 0, D0>(f[0], nx, ix, iy, bx1, by0), k0);
                 k1 = fma(P.dtqm_e[h], eval2<D0, D1, 0, 1, D0>(f[1], nx, ix, iy, bx0, by1), k1);
@@ -967,6 +975,13 @@ __device__ __noinline__ void sorted_general(Part2 &p, const FastParams<D0> &P)
         p.v[2] = fma(-P.qm_h2, g.o, p.v[2]);
         p.x[1] = pushed<1>(x_old, p.v[1], P.dt2, P.m);
     }
+    return SortedOut{p.x[1], p.v[0], p.v[1], p.v[2]};
+}
+template <int D0, int NHE, bool HP3, bool HP2>
+__device__ __forceinline__ void sorted_general(Part2 &p, const FastParams<D0> &P)
+{
+    const SortedOut o = sorted_general_v<D0, NHE, HP3, HP2>(p.x[0], p.x[1], p.v[0], p.v[1], p.v[2], p.w, P);
+    p.x[1] = o.x1; p.v[0] = o.v0; p.v[1] = o.v1; p.v[2] = o.v2;
 }
 
 // registers of one lane that persist across a cell run
@@ -1010,8 +1025,10 @@ __device__ __forceinline__ void fast_flush(FastAcc<D0, HP3, HP2> &A, int bcx, in
     }
 }
 
-template <int D0, int NHE, bool HP3, bool HP2>
-__global__ void __launch_bounds__(kThreads2, HP2 ? 2 : 3) k2_sorted(const __grid_constant__ FastParams<D0> P)
+// MINB: resident blocks per SM the register allocation aims at; PF: load the next iteration's rows before processing the
+// current one (software prefetch: 24 more live registers)
+template <int D0, int NHE, bool HP3, bool HP2, int MINB, bool PF>
+__global__ void __launch_bounds__(kThreads2, MINB) k2_sorted(const __grid_constant__ FastParams<D0> P)
 {
     using T = CellTab<D0>;
     constexpr int D1 = D0 - 1, NX0 = D0 + 1, NX1 = D1 + 1, ROWS = D1 + 3;
@@ -1035,8 +1052,10 @@ __global__ void __launch_bounds__(kThreads2, HP2 ? 2 : 3) k2_sorted(const __grid
             const int64_t ni = i + 64;
             const bool hc = ni < hi, hd = ni + 32 < hi;
             Part2 c, d;
-            if (hc) load2<void>(P.r, ni, c);
-            if (hd) load2<void>(P.r, ni + 32, d);
+            if (PF) {
+                if (hc) load2<void>(P.r, ni, c);
+                if (hd) load2<void>(P.r, ni + 32, d);
+            }
             // ---- all 64 particles in one cell?
             int cxa, cya, cxb, cyb;
             double txa, tya, txb, tyb;
@@ -1209,6 +1228,10 @@ __global__ void __launch_bounds__(kThreads2, HP2 ? 2 : 3) k2_sorted(const __grid
                 P.r.v[0][i + 32] = b.v[0];
                 P.r.v[1][i + 32] = b.v[1];
                 if (NHE > 0 || HP2) P.r.v[2][i + 32] = b.v[2];
+            }
+            if (!PF) {
+                if (hc) load2<void>(P.r, ni, c);
+                if (hd) load2<void>(P.r, ni + 32, d);
             }
             a = c; b = d;
             ha = hc; hb = hd;
@@ -1487,8 +1510,35 @@ static void build_celltab(Splitting2D &h, int nhe, double dtqm_e0, double dtqm_e
     count_launch();
 }
 
+template <int D0, int NHE, bool HP3, bool HP2, int MINB, bool PF>
+static void launch_sorted_v(Splitting2D &h, FastParams<D0> P, const char *tag);
+
+// kernel variant: GEMPIC_K2_HEAD / GEMPIC_K2_TAIL = "<blocks per SM><p|n>" (p: software prefetch), for tuning runs
+static int sorted_variant(bool head)
+{
+    static const int vh = [] { const char *e = getenv("GEMPIC_K2_HEAD"); return e ? (e[0] - '0') * 2 + (e[1] == 'p') : 2 * 2 + 1; }();
+    static const int vt = [] { const char *e = getenv("GEMPIC_K2_TAIL"); return e ? (e[0] - '0') * 2 + (e[1] == 'p') : 3 * 2 + 0; }();
+    return head ? vh : vt;
+}
+
 template <int D0, int NHE, bool HP3, bool HP2>
 static void launch_sorted(Splitting2D &h, FastParams<D0> P, const char *tag)
+{
+    if constexpr (D0 == 3) {
+        switch (sorted_variant(HP2)) {
+        case 2 * 2 + 0: return launch_sorted_v<D0, NHE, HP3, HP2, 2, false>(h, P, tag);
+        case 3 * 2 + 1: return launch_sorted_v<D0, NHE, HP3, HP2, 3, true>(h, P, tag);
+        case 3 * 2 + 0: return launch_sorted_v<D0, NHE, HP3, HP2, 3, false>(h, P, tag);
+        case 4 * 2 + 1: return launch_sorted_v<D0, NHE, HP3, HP2, 4, true>(h, P, tag);
+        case 4 * 2 + 0: return launch_sorted_v<D0, NHE, HP3, HP2, 4, false>(h, P, tag);
+        default: break;
+        }
+    }
+    launch_sorted_v<D0, NHE, HP3, HP2, 2, true>(h, P, tag);
+}
+
+template <int D0, int NHE, bool HP3, bool HP2, int MINB, bool PF>
+static void launch_sorted_v(Splitting2D &h, FastParams<D0> P, const char *tag)
 {
     Context &c = ctx();
     P.r = rows2(*h.pg);
@@ -1500,7 +1550,7 @@ static void launch_sorted(Splitting2D &h, FastParams<D0> P, const char *tag)
     P.j3 = h.j(2);
     if (P.n <= 0) return;
     int per_sm = 0;
-    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_sorted<D0, NHE, HP3, HP2>, kThreads2, 0));
+    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_sorted<D0, NHE, HP3, HP2, MINB, PF>, kThreads2, 0));
     GP_REQUIRE(per_sm >= 1, GEMPIC_EINVAL, "sorted pass does not fit on an SM");
     const int64_t warps = (int64_t)c.sm_count * per_sm * kWarps2;
     int64_t chunk = (P.n + warps * 16 - 1) / (warps * 16);
@@ -1509,7 +1559,7 @@ static void launch_sorted(Splitting2D &h, FastParams<D0> P, const char *tag)
     const int64_t n_chunks = (P.n + chunk - 1) / chunk;
     const int grid = (int)std::min<int64_t>((n_chunks + kWarps2 - 1) / kWarps2, (int64_t)c.sm_count * per_sm);
     if (tag) profile_begin(tag);
-    k2_sorted<D0, NHE, HP3, HP2><<<grid, kThreads2, 0, c.stream>>>(P);
+    k2_sorted<D0, NHE, HP3, HP2, MINB, PF><<<grid, kThreads2, 0, c.stream>>>(P);
     GP_CUDA(cudaGetLastError());
     if (tag) profile_end(tag);
     count_launch();
@@ -1527,13 +1577,14 @@ static void sorted_head(Splitting2D &h, double dt, int n_he, double dt_T)
         FastParams<D0> P{};
         P.dtqm_e[0] = 0.5 * dt * qm;
         P.dtqm_e[1] = 0.5 * dt_T * qm;
+        P.nhe = n_he;
         P.dtqm3 = 0.5 * dt * qm;
         P.wscale3 = cq * 0.5 * dt;
         P.dt2 = 0.5 * dt;
         P.qm_h2 = qm * h.maxwell->dy;
         P.wscale_h2 = cq * h.maxwell->dy;
-        if (n_he == 1) launch_sorted<D0, 1, true, true>(h, P, "fused[HE,Hp3,Hp2]{2,3}");
-        else launch_sorted<D0, 2, true, true>(h, P, "fused[HE,HE,Hp3,Hp2]{2,3}");
+        // (the kernel is the same for one or two kicks: their factors are folded into the table)
+        launch_sorted<D0, 1, true, true>(h, P, n_he == 1 ? "fused[HE,Hp3,Hp2]{2,3}" : "fused[HE,HE,Hp3,Hp2]{2,3}");
     });
     h.pg->sorted2d = false;
     allreduce_sum(h.j(1), 2 * h.nd);
