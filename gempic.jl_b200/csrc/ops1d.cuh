@@ -774,15 +774,15 @@ struct OpLoopTail {
         deposit_h<D0, LP>(acc, nh + g0, b0, ws);                          // add_charge! (OpCharge)
         double wm = p.w * P.op.mass;                                      // OpDiag, operation for operation
         wm *= P.op.cw;
-        acc.add(2 * nh + 0, (p.v1 * p.v1 + p.v2 * p.v2) * wm);
-        acc.add(2 * nh + 1, p.v1 * wm);
-        acc.add(2 * nh + 2, p.v2 * wm);
+        acc.sum(0, (p.v1 * p.v1 + p.v2 * p.v2) * wm);
+        acc.sum(1, p.v1 * wm);
+        acc.sum(2, p.v2 * wm);
         const double e1 = gather_h<D1>(sf + 2 * nh, g1, b1);
         const double e2 = gather_h<D0>(sf + 3 * nh, g0, b0);
         const double bf = gather_h<D1>(sf + 4 * nh, g1, b1);
         const double wq = P.op.charge * p.w * P.op.cw;
-        acc.add(2 * nh + 3, (p.v1 * e1 + p.v2 * e2) * wq);
-        acc.add(2 * nh + 4, wq * p.v1 * p.v2 * bf);
+        acc.sum(3, (p.v1 * e1 + p.v2 * e2) * wq);
+        acc.sum(4, wq * p.v1 * p.v2 * bf);
     }
 };
 
@@ -1101,9 +1101,9 @@ struct OpDiag {
         const int nh = P.m.n + kHalo;
         double wm = p.w * P.op.mass;
         wm *= P.op.cw;
-        acc.add(0, (p.v1 * p.v1 + p.v2 * p.v2) * wm);
-        acc.add(1, p.v1 * wm);
-        acc.add(2, p.v2 * wm);
+        acc.sum(0, (p.v1 * p.v1 + p.v2 * p.v2) * wm);
+        acc.sum(1, p.v1 * wm);
+        acc.sum(2, p.v2 * wm);
         const Pos ps = locate(p.x, P.m);
         int g0, g1;
         first_dofs<D0, D1>(ps, P.m, g0, g1);
@@ -1114,8 +1114,8 @@ struct OpDiag {
         const double e2 = gather_h<D0>(sf + nh, g0, b0);
         const double bf = gather_h<D1>(sf + 2 * nh, g1, b1);
         const double wq = P.op.charge * p.w * P.op.cw;  // get_charge
-        acc.add(3, (p.v1 * e1 + p.v2 * e2) * wq);
-        acc.add(4, wq * p.v1 * p.v2 * bf);
+        acc.sum(3, (p.v1 * e1 + p.v2 * e2) * wq);
+        acc.sum(4, wq * p.v1 * p.v2 * bf);
     }
 };
 

@@ -75,14 +75,20 @@ struct op_has_stage : std::false_type {};
 template <class Op>
 struct op_has_stage<Op, std::void_t<decltype(Op::CUSTOM_STAGE)>> : std::true_type {};
 
+constexpr int kMaxScalars = 5;
 template <bool LP>
 struct Acc {
     double *p;  // LP: warp base + lane ; ATOM: base of this warp's copy
-    __device__ __forceinline__ void add(int s, double v) const
+    // scalar sums of an Op (Op::NS <= kMaxScalars) live in registers of the thread for the whole pass and enter the
+    // accumulator slots once, before the block reduction (ncu r2e: as per-particle read-modify-writes of shared memory
+    // they were a quarter of the wavefronts of the diagnostics passes)
+    mutable double s[kMaxScalars] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    __device__ __forceinline__ void add(int slot, double v) const
     {
-        if (LP) p[s * 32] += v;
-        else atomicAdd(p + s, v);
+        if (LP) p[slot * 32] += v;
+        else atomicAdd(p + slot, v);
     }
+    __device__ __forceinline__ void sum(int k, double v) const { s[k] += v; }
 };
 
 template <class Op>
@@ -255,6 +261,11 @@ __global__ void __launch_bounds__(op_threads<Op>::value) k_pass(const __grid_con
 
     // ---- hierarchical reduce: lanes -> warps -> one partial vector per block ------------
     if (Op::DEPOSIT) {
+        if constexpr (Op::NS > 0) {
+            static_assert(Op::NS <= kMaxScalars, "scalar sums");
+#pragma unroll
+            for (int k = 0; k < Op::NS; ++k) acc.add(Op::NG * nh + k, acc.s[k]);
+        }
         __syncthreads();
         const int n_out = acc_outputs<Op>(n);
         double *out = P.partials + (size_t)blockIdx.x * n_out;
