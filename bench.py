@@ -75,7 +75,7 @@ BYTES = {"operatorHE": 40, "operatorHp2": 40, "operatorHp1": 48, "operatorHp1+rh
          "operatorHE+j2": 48, "j2 deposit": 24, "add_charge": 16, "write_step sums": 32, "loop tail [HE,rho,diag]": 48,
          # 2d3v rows x1,x2,v1,v2,v3,w: HE 40 R + 24 W, Hp3 48 R + 16 W, Hp1/Hp2 48 R + 24 W; sort 2 x 48 + keys
          "fused[HE,Hp3]{2,3}": 72, "fused[HE,HE,Hp3]{2,3}": 72, "operatorHE{2,3}": 64, "operatorHp3{2,3}": 64,
-         "operatorHp1{2,3}": 72, "operatorHp2{2,3}": 72, "cell sort 2d": 112, "operatorHp2{2,3}+sort": 96,
+         "operatorHp1{2,3}": 72, "operatorHp1{2,3}+hist": 72, "operatorHp2{2,3}": 72, "cell sort 2d": 112, "operatorHp2{2,3}+sort": 96,
          "cell histogram after Hp2": 24, "fused[HE,Hp3,Hp2]{2,3}": 80, "fused[HE,HE,Hp3,Hp2]{2,3}": 80, "operatorHp3{2,3} sorted": 64,
          "fused[Hp1,Hp2,Hp3]{2,3}+sort": 96, "fused[Hp1,Hp2,Hp3]{2,3}": 72, "add_charge2d": 24}
 STEP_BYTES = {"hs": 208, "boris": 160, "hs2d": 2 * 64 + 2 * 64 + 3 * 72}   # one pass per reference operator

@@ -449,10 +449,18 @@ struct Op2HEHp3 {
 // as in OpStrangFused); across DIR the degree-p (j, B2/B1) and degree-(p-1) (B3) splines are evaluated.
 // SORT: the pass writes every particle (all rows) to its cell-sorted place in the other buffer instead of updating it in
 // place -- the periodic cell sort rides in the last push of a Strang step (k2_pass, sorting_hp2).
-template <int D0, int DIR, bool SORT = false>
+// HIST (operatorHp1 only): the pass also histograms the cell-sort keys the particles will have after the operatorHp2 push
+// that follows (dt_next) -- every input of that push is final once Hp1 is done -- which saves the separate 24 B/particle
+// histogram pass of the riding sort.
+template <int D0, int DIR, bool SORT = false, bool HIST_ = false>
 struct Op2Hp12 {
     static __device__ __forceinline__ double stage(const P2<Op2Hp12> &P, int f, size_t g) { return P.f[f][g]; }
-    static constexpr bool DEPOSIT = true, WRITE_X = true, WRITE_V = true, SCATTER = SORT;
+    static constexpr bool DEPOSIT = true, WRITE_X = true, WRITE_V = true, SCATTER = SORT, HIST = HIST_;
+    // cell-sort key of the particle after the NEXT operatorHp2 push (HIST)
+    static __device__ __forceinline__ int key_next(const Part2 &p, const P2<Op2Hp12> &P)
+    {
+        return sort_key2(p.x[0], pushed<1>(p.x[1], p.v[1], P.op.dt_next, P.m), P.m);
+    }
     // cell-sort key of the particle after this push (SCATTER)
     static __device__ __forceinline__ int key_after(const Part2 &p, const P2<Op2Hp12> &P)
     {
@@ -460,7 +468,7 @@ struct Op2Hp12 {
         return DIR == 0 ? sort_key2(xn, p.x[1], P.m) : sort_key2(p.x[0], xn, P.m);
     }
     static constexpr int D = D0, NF = 2;
-    struct Params { double dt, qm_h, wscale_h; };   // h = d[DIR]
+    struct Params { double dt, qm_h, wscale_h, dt_next; };   // h = d[DIR]
     using PP = P2<Op2Hp12>;
 
     // general path: any displacement, global loads and REDs (rare: more than one cell per step or outside the window)
@@ -669,6 +677,18 @@ __global__ void __launch_bounds__(256) k2_hist_after_hp2(Rows2 r, int64_t n, dou
     }
 }
 
+template <class Op, class = void>
+struct op_hist : std::false_type {};
+template <class Op>
+struct op_hist<Op, std::enable_if_t<Op::HIST>> : std::true_type {};
+// hist[key] += 1 for the converged lanes, one atomic per distinct key
+__device__ __forceinline__ void hist_add(int *__restrict__ hist, int key, int lane)
+{
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, key);
+    if (lane == __ffs(peers) - 1) atomicAdd(hist + key, __popc(peers));
+}
+
 // shared memory of one warp: Op::NF field tiles (W*W doubles each, shared by the lanes) followed by the
 // lane-private deposit tile (W*W*32 doubles)
 template <class Op>
@@ -755,9 +775,11 @@ __global__ void __launch_bounds__(kThreads2, 3) k2_pass(const __grid_constant__ 
             if (hd) load2<Op>(P.r, ni + 32, d);
             Op::apply(a, P, ftile, tile, bx, by);
             store2<Op>(P.r, i, a);
+            if constexpr (op_hist<Op>::value) hist_add(P.cursor, Op::key_next(a, P), lane);
             if (hb) {
                 Op::apply(b, P, ftile, tile, bx, by);
                 store2<Op>(P.r, i + 32, b);
+                if constexpr (op_hist<Op>::value) hist_add(P.cursor, Op::key_next(b, P), lane);
             }
             a = c; b = d;
             ha = hc; hb = hd;
@@ -1397,10 +1419,37 @@ static void op2_Hp12(Splitting2D &h, double dt)
     m2d_e_from_j(*h.maxwell, h.e(DIR), h.j(DIR), DIR + 1);
 }
 
-// operatorHp2 that leaves the particles cell sorted: histogram of the cells after the push -> scan -> the push pass
-// places every particle (all rows) at its sorted position in the other buffer -> swap.  24 + 96 B/particle instead of
-// 72 (push in place) + 112 (stand-alone sort).
-static void sorting_hp2(Splitting2D &h, double dt)
+// operatorHp1 that also histograms the sort keys after the operatorHp2(dt_next) push that follows (Op2Hp12 HIST)
+static void op2_Hp1_with_hist(Splitting2D &h, double dt, double dt_next)
+{
+    Context &c = ctx();
+    ParticleGroup &pg = *h.pg;
+    const int cells = (int)h.nd;
+    if (pg.sort_keys.n < (size_t)cells) pg.sort_keys.alloc(cells);
+    GP_CUDA(cudaMemsetAsync(pg.sort_keys.p, 0, sizeof(int) * cells, c.stream));
+    zero_grid(h.j(0), h.nd);
+    GP_DISPATCH_D0(h.maxwell->s_deg_0, {
+        P2<Op2Hp12<D0, 0, false, true>> P{};
+        P.f[0] = h.b(2);
+        P.f[1] = h.b(1);
+        P.grid = h.j(0);
+        P.cursor = pg.sort_keys.p;
+        P.op.dt = dt;
+        P.op.qm_h = pg.q_over_m * h.maxwell->dx;
+        P.op.wscale_h = pg.charge * pg.common_weight * h.maxwell->dx;
+        P.op.dt_next = dt_next;
+        launch2(h, P, "operatorHp1{2,3}+hist");
+    });
+    pg.sorted2d = false;
+    allreduce_sum(h.j(0), h.nd);
+    m2d_e_from_j(*h.maxwell, h.e(0), h.j(0), 1);
+}
+
+// operatorHp2 that leaves the particles cell sorted: histogram of the cells after the push (taken by the preceding
+// operatorHp1 pass when have_hist, else by k2_hist_after_hp2) -> scan -> the push pass places every particle (all rows)
+// at its sorted position in the other buffer -> swap.  96 (+ 24) B/particle instead of 72 (push in place) + 112
+// (stand-alone sort).
+static void sorting_hp2(Splitting2D &h, double dt, bool have_hist = false)
 {
     Context &c = ctx();
     ParticleGroup &pg = *h.pg;
@@ -1409,17 +1458,19 @@ static void sorting_hp2(Splitting2D &h, double dt)
     if (pg.sort_keys.n < (size_t)cells) pg.sort_keys.alloc(cells);
     if (pg.sort_tmp.n < pg.data.n) pg.sort_tmp.alloc(pg.data.n);
     int *hist = pg.sort_keys.p;
-    GP_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * cells, c.stream));
     const Mesh2 m = mesh2(*h.maxwell);
-    const size_t hsmem = (size_t)cells * sizeof(int);
-    GP_REQUIRE(hsmem <= kSmemMaxOptin, GEMPIC_EINVAL, "riding sort: %d cells exceed the shared-memory histogram", cells);
-    if (hsmem > 48 * 1024) ensure_func_smem((const void *)k2_hist_after_hp2, hsmem);
-    profile_begin("cell histogram after Hp2");
-    const int hgrid = (int)std::min<int64_t>((int64_t)c.sm_count * 8, (pg.n + 255) / 256);
-    k2_hist_after_hp2<<<hgrid, 256, hsmem, c.stream>>>(rows2(pg), pg.n, dt, m, cells, hist);
-    GP_CUDA(cudaGetLastError());
-    profile_end("cell histogram after Hp2");
-    count_launch();
+    if (!have_hist) {
+        GP_CUDA(cudaMemsetAsync(hist, 0, sizeof(int) * cells, c.stream));
+        const size_t hsmem = (size_t)cells * sizeof(int);
+        GP_REQUIRE(hsmem <= kSmemMaxOptin, GEMPIC_EINVAL, "riding sort: %d cells exceed the shared-memory histogram", cells);
+        if (hsmem > 48 * 1024) ensure_func_smem((const void *)k2_hist_after_hp2, hsmem);
+        profile_begin("cell histogram after Hp2");
+        const int hgrid = (int)std::min<int64_t>((int64_t)c.sm_count * 8, (pg.n + 255) / 256);
+        k2_hist_after_hp2<<<hgrid, 256, hsmem, c.stream>>>(rows2(pg), pg.n, dt, m, cells, hist);
+        GP_CUDA(cudaGetLastError());
+        profile_end("cell histogram after Hp2");
+        count_launch();
+    }
     sort_scan(hist, cells);
     // rows of the other buffer
     Rows2 dst;
@@ -1648,9 +1699,13 @@ static void strang2d_fused(Splitting2D &h, double dt, int64_t steps)
             else fused_he_hp3(h, dt, 2, dt);
         }
         if (!fast) hs2d_operator(h, GEMPIC_OP_HP2, 0.5 * dt);
-        hs2d_operator(h, GEMPIC_OP_HP1, dt);
-        if (ride) sorting_hp2(h, 0.5 * dt);
-        else hs2d_operator(h, GEMPIC_OP_HP2, 0.5 * dt);
+        if (ride) {   // the Hp1 pass also takes the histogram of the sort keys after the Hp2 push that follows
+            op2_Hp1_with_hist(h, dt, 0.5 * dt);
+            sorting_hp2(h, 0.5 * dt, true);
+        } else {
+            hs2d_operator(h, GEMPIC_OP_HP1, dt);
+            hs2d_operator(h, GEMPIC_OP_HP2, 0.5 * dt);
+        }
         if (fast) sorted_hp3(h, 0.5 * dt);
         else hs2d_operator(h, GEMPIC_OP_HP3, 0.5 * dt);
         h.steps_done++;
