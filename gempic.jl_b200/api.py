@@ -133,15 +133,23 @@ class ParticleGroup(_Handle):
 
     @property
     def array(self):
-        """Host view (rows, N). Reading it downloads if the device is ahead; because the caller
-        may write into it, the next device operation uploads it again."""
+        """Host view (rows, N). Reading it downloads if the device is ahead; because the caller may write into it, the
+        next device operation uploads it again.  The view is only coherent until the next device operation: fetch
+        `pg.array` again afterwards (a numpy view kept across a device call is neither refreshed nor uploaded; the Julia
+        shim's MirrorArray tracks this, numpy cannot)."""
+        a = self._mirror()
+        self._host_newer = True
+        return a
+
+    def _mirror(self):
+        """the host mirror for READING: synchronised with the device, not marked as written (get_x / get_v /
+        get_charge / get_mass go through here, so a read-only diagnostic loop never re-uploads the particles)"""
         if self._host is None:
             self._host = np.zeros((self.n_particles, self.rows))
             self._dev_newer = True
         if self._dev_newer:
             check(_L().gempic_pg_download(self._h, dptr(self._host)))
             self._dev_newer = False
-        self._host_newer = True
         return self._host.T
 
     def to_host(self):
@@ -170,19 +178,19 @@ class ParticleGroup(_Handle):
 
     # -- reference accessors (particle_group.jl:53-150) --------------------------------------
     def get_x(self, i):
-        return self.array[0:self.dims[0], i].copy()
+        return self._mirror()[0:self.dims[0], i].copy()
 
     def get_v(self, i):
         D, V = self.dims
-        return self.array[D:D + V, i].copy()
+        return self._mirror()[D:D + V, i].copy()
 
     def get_charge(self, i, i_wi=1):
         D, V = self.dims
-        return self.charge * self.array[D + V + i_wi - 1, i] * self.common_weight
+        return self.charge * self._mirror()[D + V + i_wi - 1, i] * self.common_weight
 
     def get_mass(self, i, i_wi=1):
         D, V = self.dims
-        return self.mass * self.array[D + V + i_wi - 1, i] * self.common_weight
+        return self.mass * self._mirror()[D + V + i_wi - 1, i] * self.common_weight
 
     def set_x(self, i, x):
         x = np.atleast_1d(np.asarray(x, dtype=np.float64))

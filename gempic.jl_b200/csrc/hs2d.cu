@@ -1669,7 +1669,10 @@ static void strang2d_fused(Splitting2D &h, double dt, int64_t steps)
     const double *e[3] = {h.e(0), h.e(1), h.e(2)};
     // sort_interval == 1: the cell sort rides in the last push of every step (sorting_hp2); a stand-alone sort is only
     // needed when somebody else has moved the particles since
-    const bool ride = h.sort_interval == 1 && h.pg->W == 1 && h.pg->n >= 2;
+    // grids beyond the cell sort's shared-memory histogram (51200 cells) run un-sorted: the tile passes then take their
+    // general path more often, but nothing fails
+    const bool sortable = h.nd * sizeof(int) <= 200 * 1024;
+    const bool ride = sortable && h.sort_interval == 1 && h.pg->W == 1 && h.pg->n >= 2;
     // fuse level 2: the operators that start from the sorted order run on the register-resident fast path (k2_sorted)
     const bool fast = ride && h.fuse >= 2;
     // a trailing HE kick this splitting left pending in its previous call (fields already advanced, snapshot in eT)
@@ -1681,7 +1684,7 @@ static void strang2d_fused(Splitting2D &h, double dt, int64_t steps)
     for (int64_t s = 0; s < steps; ++s) {
         if (ride) {
             if (!h.pg->sorted2d) pg_sort_2d(*h.pg, *h.maxwell);
-        } else if (h.sort_interval > 0 && h.steps_done % h.sort_interval == 0) {
+        } else if (sortable && h.sort_interval > 0 && h.steps_done % h.sort_interval == 0) {
             pg_sort_2d(*h.pg, *h.maxwell);
         }
         if (s == 0) {
@@ -1736,7 +1739,7 @@ void hs2d_strang(Splitting2D &h, double dt, int64_t steps)
     }
     pg_sync(*h.pg);
     for (int64_t s = 0; s < steps; ++s) {
-        if (h.sort_interval > 0 && h.steps_done % h.sort_interval == 0) pg_sort_2d(*h.pg, *h.maxwell);
+        if (h.nd * sizeof(int) <= 200 * 1024 && h.sort_interval > 0 && h.steps_done % h.sort_interval == 0) pg_sort_2d(*h.pg, *h.maxwell);
         hs2d_operator(h, GEMPIC_OP_HB, 0.5 * dt);
         hs2d_operator(h, GEMPIC_OP_HE, 0.5 * dt);
         hs2d_operator(h, GEMPIC_OP_HP3, 0.5 * dt);
