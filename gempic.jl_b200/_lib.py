@@ -86,6 +86,21 @@ def init(device: int | None = None):
         device = int(os.environ.get("LOCAL_RANK", "0"))
     check(load().gempic_init(C.c_int(device)))
     _initialised = True
+    _register_atexit()
+
+
+_atexit_done = False
+
+
+def _register_atexit():
+    """finalise the library before the interpreter tears its objects down in arbitrary order (and, after
+    init_devices, join the per-device worker threads)"""
+    global _atexit_done
+    if not _atexit_done:
+        import atexit
+
+        atexit.register(finalize)
+        _atexit_done = True
 
 
 def init_devices(devices):
@@ -99,6 +114,7 @@ def init_devices(devices):
     arr = (C.c_int * len(ids))(*ids)
     check(load().gempic_init_devices(C.c_int(len(ids)), arr))
     _initialised = True
+    _register_atexit()
 
 
 def device_count() -> int:

@@ -63,6 +63,7 @@ struct Rank {
     std::vector<cudaEvent_t> event_pool;
     std::unordered_map<const void *, size_t> func_smem;
     bool host_out = true;
+    ~Rank();   // ordered teardown at process exit when gempic_finalize was not called
 };
 static Rank g_rank0;
 static thread_local Rank *t_rank = &g_rank0;
@@ -149,6 +150,20 @@ void destroy(gempic_handle h, Kind kind, const char *what)
     }
     if (g_ctx.ready) cudaStreamSynchronize(g_ctx.stream);
 }   // `victim` (and, through its destructor, the releases of what it retained) goes here, outside the lock
+
+// A process may exit without gempic_finalize (a script that simply ends).  The registry then goes down with the static
+// Rank: the splitting objects must go first (their destructors release what they point to, which walks this rank's
+// zombie list), and release() must find THIS rank whatever thread runs the destructor.
+Rank::~Rank()
+{
+    Rank *saved = t_rank;
+    t_rank = this;
+    try {
+        destroy_all();
+    } catch (...) {
+    }
+    t_rank = saved == this ? &g_rank0 : saved;
+}
 
 void destroy_all()
 {
@@ -501,7 +516,11 @@ struct Worker {
     int rc = 0;
     std::string err;
 };
-static std::vector<std::unique_ptr<Worker>> g_workers;
+static void stop_workers();
+struct WorkerList : std::vector<std::unique_ptr<Worker>> {
+    ~WorkerList() { stop_workers(); }   // exit without gempic_finalize: the threads must be joined before they are destroyed
+};
+static WorkerList g_workers;
 static thread_local bool t_in_worker = false;
 
 static void worker_main(Worker *w)
