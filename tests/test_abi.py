@@ -56,6 +56,19 @@ def test_fails_loudly_without_gpu(gp):
         gp.ParticleGroup(1, 2, 4)
 
 
+def test_init_devices_fails_loudly_without_gpu(gp):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = gp.load()
+    ids = (ctypes.c_int * 2)(0, 1)
+    assert lib.gempic_init_devices(ctypes.c_int(2), ids) == 6        # GEMPIC_ENOTINIT: no CPU path in this mode either
+    assert lib.gempic_device_count() == 1
+    with pytest.raises(gp.GempicError):
+        gp.init_devices(2)
+
+
 def test_product_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "gempic.jl_b200")
     for dirpath, _, files in os.walk(pkg):
