@@ -1047,9 +1047,51 @@ __device__ __forceinline__ void fast_flush(FastAcc<D0, HP3, HP2> &A, int bcx, in
     }
 }
 
-// MINB: resident blocks per SM the register allocation aims at; PF: load the next iteration's rows before processing the
-// current one (software prefetch: 24 more live registers)
-template <int D0, int NHE, bool HP3, bool HP2, int MINB, bool PF>
+// ---- TMA row stream (PF == 2): every warp runs its own kTmaStages-deep pipeline of bulk copies (cp.async.bulk, one per
+// particle row and stage, 64 particles each) into shared memory, completion tracked by one mbarrier per stage.  The loads
+// of the next kTmaStages iterations are in flight whatever the register budget; lane 0 issues, all lanes wait.
+constexpr int kTmaStages = 4, kTmaRows = 6, kTmaTile = 64;
+constexpr size_t kTmaWarpBytes = (size_t)kTmaStages * kTmaRows * kTmaTile * sizeof(double) + kTmaStages * sizeof(unsigned long long);
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// lane 0: arm stage `st` and start the six row copies of the 64-particle tile that begins at particle i0
+__device__ __forceinline__ void tma_issue(const Rows2 &r, double *buf, unsigned long long *bars, int st, int64_t i0, int64_t hi)
+{
+    const int cnt = (int)min((int64_t)kTmaTile, hi - i0);
+    const unsigned bytes = (unsigned)(((cnt + 1) & ~1) * sizeof(double));   // 16-byte granules (rows are padded to 32 doubles)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // the tile's previous contents have been read
+    mbar_expect_tx(bars + st, kTmaRows * bytes);
+    double *dst = buf + (size_t)st * kTmaRows * kTmaTile;
+    const double *src[kTmaRows] = {r.x[0], r.x[1], r.v[0], r.v[1], r.v[2], r.w};
+#pragma unroll
+    for (int q = 0; q < kTmaRows; ++q) bulk_g2s(dst + q * kTmaTile, src[q] + i0, bytes, bars + st);
+}
+
+// MINB: resident blocks per SM the register allocation aims at; PF: 0 plain loads, 1 the next iteration's rows are loaded
+// into registers before the current one is processed (software prefetch: 24 more live registers), 2 TMA row stream
+template <int D0, int NHE, bool HP3, bool HP2, int MINB, int PF>
 __global__ void __launch_bounds__(kThreads2, MINB) k2_sorted(const __grid_constant__ FastParams<D0> P)
 {
     using T = CellTab<D0>;
@@ -1062,19 +1104,57 @@ __global__ void __launch_bounds__(kThreads2, MINB) k2_sorted(const __grid_consta
     for (int q = 0; q < A.N3; ++q) A.a3[q] = 0.0;
 #pragma unroll
     for (int q = 0; q < A.N2; ++q) A.a2[q] = 0.0;
+    // TMA row stream: this warp's stage buffers and barriers
+    extern __shared__ __align__(128) unsigned char k2s_smem[];
+    double *tbuf = nullptr;
+    unsigned long long *tbar = nullptr;
+    unsigned tcount = 0;   // tiles consumed so far by this warp: stage = tcount % kTmaStages, parity = (tcount / kTmaStages) & 1
+    if constexpr (PF == 2) {
+        tbuf = reinterpret_cast<double *>(k2s_smem + (size_t)warp * kTmaWarpBytes);
+        tbar = reinterpret_cast<unsigned long long *>(tbuf + (size_t)kTmaStages * kTmaRows * kTmaTile);
+        if (lane == 0) {
+#pragma unroll
+            for (int st = 0; st < kTmaStages; ++st) mbar_init(tbar + st, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     for (int64_t ch = (int64_t)blockIdx.x * kWarps2 + warp; ch < n_chunks; ch += (int64_t)gridDim.x * kWarps2) {
         const int64_t lo = ch * P.chunk, hi = min(P.n, lo + P.chunk);
         int bcx = -1, bcy = -1;   // cell the register accumulators belong to
         int64_t i = lo + lane;
         Part2 a, b;
         bool ha = i < hi, hb = i + 32 < hi;
-        if (ha) load2<void>(P.r, i, a);
-        if (hb) load2<void>(P.r, i + 32, b);
+        if constexpr (PF == 2) {
+            if (lane == 0) {
+#pragma unroll
+                for (int st = 0; st < kTmaStages; ++st)
+                    if (lo + (int64_t)st * kTmaTile < hi) tma_issue(P.r, tbuf, tbar, (tcount + st) % kTmaStages, lo + (int64_t)st * kTmaTile, hi);
+            }
+        } else {
+            if (ha) load2<void>(P.r, i, a);
+            if (hb) load2<void>(P.r, i + 32, b);
+        }
         while (__any_sync(0xffffffffu, ha)) {
             const int64_t ni = i + 64;
             const bool hc = ni < hi, hd = ni + 32 < hi;
             Part2 c, d;
-            if (PF) {
+            if constexpr (PF == 2) {
+                // wait for the tile of this iteration, take the two particles of the lane, hand the stage back to the copies
+                const int st = tcount % kTmaStages;
+                const unsigned parity = (tcount / kTmaStages) & 1u;
+                unsigned spins = 0;
+                while (!mbar_try_wait(tbar + st, parity))
+                    if (++spins > (1u << 26)) __trap();   // a lost copy must not hang the GPU
+                const double *t = tbuf + (size_t)st * kTmaRows * kTmaTile;
+                if (ha) { a.x[0] = t[lane]; a.x[1] = t[kTmaTile + lane]; a.v[0] = t[2 * kTmaTile + lane]; a.v[1] = t[3 * kTmaTile + lane]; a.v[2] = t[4 * kTmaTile + lane]; a.w = t[5 * kTmaTile + lane]; }
+                if (hb) { b.x[0] = t[32 + lane]; b.x[1] = t[kTmaTile + 32 + lane]; b.v[0] = t[2 * kTmaTile + 32 + lane]; b.v[1] = t[3 * kTmaTile + 32 + lane]; b.v[2] = t[4 * kTmaTile + 32 + lane]; b.w = t[5 * kTmaTile + 32 + lane]; }
+                __syncwarp();
+                const int64_t i_next = (i - lane) + (int64_t)kTmaStages * kTmaTile;
+                if (lane == 0 && i_next < hi) tma_issue(P.r, tbuf, tbar, st, i_next, hi);
+                ++tcount;
+            }
+            if constexpr (PF == 1) {
                 if (hc) load2<void>(P.r, ni, c);
                 if (hd) load2<void>(P.r, ni + 32, d);
             }
@@ -1251,11 +1331,11 @@ __global__ void __launch_bounds__(kThreads2, MINB) k2_sorted(const __grid_consta
                 P.r.v[1][i + 32] = b.v[1];
                 if (NHE > 0 || HP2) P.r.v[2][i + 32] = b.v[2];
             }
-            if (!PF) {
+            if constexpr (PF == 0) {
                 if (hc) load2<void>(P.r, ni, c);
                 if (hd) load2<void>(P.r, ni + 32, d);
             }
-            a = c; b = d;
+            if constexpr (PF != 2) { a = c; b = d; }
             ha = hc; hb = hd;
             i = ni;
         }
@@ -1561,14 +1641,20 @@ static void build_celltab(Splitting2D &h, int nhe, double dtqm_e0, double dtqm_e
     count_launch();
 }
 
-template <int D0, int NHE, bool HP3, bool HP2, int MINB, bool PF>
+template <int D0, int NHE, bool HP3, bool HP2, int MINB, int PF>
 static void launch_sorted_v(Splitting2D &h, FastParams<D0> P, const char *tag);
 
-// kernel variant: GEMPIC_K2_HEAD / GEMPIC_K2_TAIL = "<blocks per SM><p|n>" (p: software prefetch), for tuning runs
+// kernel variant: GEMPIC_K2_HEAD / GEMPIC_K2_TAIL = "<blocks per SM><n|p|t>" (n: plain loads, p: register prefetch,
+// t: TMA row stream), for tuning runs; code = blocks * 3 + fetch mode
 static int sorted_variant(bool head)
 {
-    static const int vh = [] { const char *e = getenv("GEMPIC_K2_HEAD"); return e ? (e[0] - '0') * 2 + (e[1] == 'p') : 2 * 2 + 1; }();
-    static const int vt = [] { const char *e = getenv("GEMPIC_K2_TAIL"); return e ? (e[0] - '0') * 2 + (e[1] == 'p') : 3 * 2 + 0; }();
+    auto parse = [](const char *name, int dflt) {
+        const char *e = getenv(name);
+        if (!e || !e[0] || !e[1]) return dflt;
+        return (e[0] - '0') * 3 + (e[1] == 'p' ? 1 : e[1] == 't' ? 2 : 0);
+    };
+    static const int vh = parse("GEMPIC_K2_HEAD", 2 * 3 + 1);
+    static const int vt = parse("GEMPIC_K2_TAIL", 3 * 3 + 2);
     return head ? vh : vt;
 }
 
@@ -1577,21 +1663,24 @@ static void launch_sorted(Splitting2D &h, FastParams<D0> P, const char *tag)
 {
     if constexpr (D0 == 3) {
         switch (sorted_variant(HP2)) {
-        case 2 * 2 + 0: return launch_sorted_v<D0, NHE, HP3, HP2, 2, false>(h, P, tag);
-        case 3 * 2 + 1: return launch_sorted_v<D0, NHE, HP3, HP2, 3, true>(h, P, tag);
-        case 3 * 2 + 0: return launch_sorted_v<D0, NHE, HP3, HP2, 3, false>(h, P, tag);
-        case 4 * 2 + 1: return launch_sorted_v<D0, NHE, HP3, HP2, 4, true>(h, P, tag);
-        case 4 * 2 + 0: return launch_sorted_v<D0, NHE, HP3, HP2, 4, false>(h, P, tag);
+        case 2 * 3 + 0: return launch_sorted_v<D0, NHE, HP3, HP2, 2, 0>(h, P, tag);
+        case 2 * 3 + 2: return launch_sorted_v<D0, NHE, HP3, HP2, 2, 2>(h, P, tag);
+        case 3 * 3 + 0: return launch_sorted_v<D0, NHE, HP3, HP2, 3, 0>(h, P, tag);
+        case 3 * 3 + 1: return launch_sorted_v<D0, NHE, HP3, HP2, 3, 1>(h, P, tag);
+        case 3 * 3 + 2: return launch_sorted_v<D0, NHE, HP3, HP2, 3, 2>(h, P, tag);
+        case 4 * 3 + 2: return launch_sorted_v<D0, NHE, HP3, HP2, 4, 2>(h, P, tag);
         default: break;
         }
     }
-    launch_sorted_v<D0, NHE, HP3, HP2, 2, true>(h, P, tag);
+    launch_sorted_v<D0, NHE, HP3, HP2, 2, 1>(h, P, tag);
 }
 
-template <int D0, int NHE, bool HP3, bool HP2, int MINB, bool PF>
+template <int D0, int NHE, bool HP3, bool HP2, int MINB, int PF>
 static void launch_sorted_v(Splitting2D &h, FastParams<D0> P, const char *tag)
 {
     Context &c = ctx();
+    const size_t smem = PF == 2 ? (size_t)kWarps2 * kTmaWarpBytes : 0;
+    if (smem > 48 * 1024) ensure_func_smem((const void *)k2_sorted<D0, NHE, HP3, HP2, MINB, PF>, smem);
     P.r = rows2(*h.pg);
     P.n = h.pg->n;
     P.m = mesh2(*h.maxwell);
@@ -1601,7 +1690,7 @@ static void launch_sorted_v(Splitting2D &h, FastParams<D0> P, const char *tag)
     P.j3 = h.j(2);
     if (P.n <= 0) return;
     int per_sm = 0;
-    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_sorted<D0, NHE, HP3, HP2, MINB, PF>, kThreads2, 0));
+    GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_sorted<D0, NHE, HP3, HP2, MINB, PF>, kThreads2, smem));
     GP_REQUIRE(per_sm >= 1, GEMPIC_EINVAL, "sorted pass does not fit on an SM");
     const int64_t warps = (int64_t)c.sm_count * per_sm * kWarps2;
     int64_t chunk = (P.n + warps * 16 - 1) / (warps * 16);
@@ -1610,7 +1699,7 @@ static void launch_sorted_v(Splitting2D &h, FastParams<D0> P, const char *tag)
     const int64_t n_chunks = (P.n + chunk - 1) / chunk;
     const int grid = (int)std::min<int64_t>((n_chunks + kWarps2 - 1) / kWarps2, (int64_t)c.sm_count * per_sm);
     if (tag) profile_begin(tag);
-    k2_sorted<D0, NHE, HP3, HP2, MINB, PF><<<grid, kThreads2, 0, c.stream>>>(P);
+    k2_sorted<D0, NHE, HP3, HP2, MINB, PF><<<grid, kThreads2, smem, c.stream>>>(P);
     GP_CUDA(cudaGetLastError());
     if (tag) profile_end(tag);
     count_launch();

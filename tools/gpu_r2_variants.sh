@@ -1,7 +1,7 @@
 #!/bin/bash
 # tuning visit: register / prefetch variants of the sorted 2d3v passes (k2_sorted), one short bench each
 OUT=gpurun_out; mkdir -p $OUT
-for V in "2p 3p" "2n 3n" "2p 2p" "2n 2n" "3p 4p" "3n 4n"; do
+for V in "2p 3n" "2t 3t" "2t 2t" "2p 4t"; do
   set -- $V
   GEMPIC_K2_HEAD=$1 GEMPIC_K2_TAIL=$2 timeout 300 python bench.py --workload 2d3v --steps 6 --no-cpu --no-configs --min-seconds 0.2 > $OUT/var.json 2> $OUT/var.err
   python - "$1" "$2" <<'PY'
