@@ -526,6 +526,7 @@ def e2e_loop_1d(B, S, steps):
     return {"value": S["n_global"] * steps / sec, "unit": "particle-steps/s", "steps": steps,
             "particle_bytes_per_step": bytes_pp,
             "passes_per_step": {k: v[1] / steps for k, v in prof.items() if v[1]},
+            "pass_ms": {k: v[0] / v[1] for k, v in prof.items() if v[1]}, "ms_per_step": sec / steps * 1e3,
             "h2d_bytes_per_step": (3 + 6) * NX * 8, "d2h_bytes_per_step": (3 + 2) * NX * 8 + 11 * 8,
             "what": "strang_splitting!(h, dt, 1); solve_poisson!; write_step! per step, host buffers, synchronous"}
 

@@ -59,6 +59,9 @@ struct Context {
     unsigned long long xchg_seq = 0;
     double *pinned = nullptr;  // small pinned staging buffer for field I/O
     size_t pinned_bytes = 0;
+    double *stage = nullptr;   // grow-only device scratch of the host-buffer entry points (hostutil.hpp Stage)
+    size_t stage_n = 0;
+    bool stage_busy = false;
 };
 Context &ctx();   // of the calling thread's rank (one per process, or one per device after gempic_init_devices)
 void require_init();

@@ -7,14 +7,44 @@
 
 namespace gempic {
 
-// host vectors of n doubles staged into one scratch allocation
+// host vectors of n doubles staged into one scratch allocation.  The scratch is the rank's grow-only buffer
+// (Context::stage): a cudaMalloc + cudaFree per API call costs more than the small kernels it serves and synchronises
+// the device (the diagnostics loop calls write_step! every step).  A second Stage alive at the same time gets its own.
 struct Stage {
-    DevBuf<double> buf;
+    DevBuf<double> own;
+    double *base = nullptr;
     size_t used = 0;
-    explicit Stage(size_t total) : buf(total ? total : 1) {}
+    bool shared = false;
+    explicit Stage(size_t total)
+    {
+        Context &c = ctx();
+        if (!total) total = 1;
+        if (!c.stage_busy && total <= ((size_t)1 << 22)) {   // up to 32 MB is kept; per-particle arrays come and go
+            if (c.stage_n < total) {
+                if (c.stage) cudaFree(c.stage);   // synchronises: nothing in flight still reads it
+                c.stage = nullptr;
+                c.stage_n = 0;
+                const size_t n = total < 4096 ? 4096 : total;
+                GP_CUDA(cudaMalloc(&c.stage, n * sizeof(double)));
+                c.stage_n = n;
+            }
+            base = c.stage;
+            shared = true;
+            c.stage_busy = true;
+        } else {
+            own.alloc(total);
+            base = own.p;
+        }
+    }
+    Stage(const Stage &) = delete;
+    Stage &operator=(const Stage &) = delete;
+    ~Stage()
+    {
+        if (shared) ctx().stage_busy = false;
+    }
     double *take(size_t n)
     {
-        double *p = buf.p + used;
+        double *p = base + used;
         used += n;
         return p;
     }

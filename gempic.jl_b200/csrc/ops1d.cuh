@@ -39,6 +39,17 @@ __device__ __forceinline__ double gather_h(const double *__restrict__ field, int
     return v;
 }
 
+// the same gather on a field staged in S lane-interleaved copies (Op::FIELD_COPIES = S, pass.cuh): element g of the
+// calling lane's copy sits S doubles after element g-1, so a half-warp's gather is conflict free for any cell pattern
+template <int D, int S>
+__device__ __forceinline__ double gather_hs(const double *__restrict__ field, int g0, const double (&b)[D + 1])
+{
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k <= D; ++k) v = fma(field[(g0 + k) * S], b[k], v);
+    return v;
+}
+
 // grid[g0+k] += ws * N_k   with ws = marker charge * scaling   (add_charge!, pmc1d.jl:261-280)
 template <int D, bool LP>
 __device__ __forceinline__ void deposit_h(const Acc<LP> &acc, int slot0, const double (&b)[D + 1], double ws)
@@ -757,6 +768,10 @@ struct OpLoopTail {
     static constexpr int READ = ROW_X | ROW_V1 | ROW_V2 | ROW_W, WRITE = ROW_V1 | ROW_V2;
     static constexpr int NF = 5, NG = 2, NS = 5;
     static constexpr bool DEPOSIT = true;
+    // 16 lane-interleaved copies of the five gathered fields: with one copy, 29 % of the shared-memory wavefronts of
+    // this pass were bank conflicts of the gathers (ncu r2e; 32 lanes reading random cells of 36-double vectors)
+    static constexpr int FIELD_COPIES = 16;
+    static constexpr int FC = FIELD_COPIES;
     struct Params { double dtqm, wscale0, charge, mass, cw; };
     template <bool LP>
     static __device__ __forceinline__ void apply(Particle &p, const PassParams<OpLoopTail> &P, const double *sf, const Acc<LP> &acc)
@@ -770,16 +785,17 @@ struct OpLoopTail {
         basis_pp<D0>(ps.t, b0);
         const double ws = p.w * P.op.wscale0;
         deposit_h<D0, LP>(acc, g0, b0, ws * p.v2);                       // j_dofs[2] before the kick (OpHEJ2)
-        kick_e<D0, D1>(p, g0, g1, b0, b1, sf, sf + nh, P.op.dtqm);
+        p.v1 = fma(P.op.dtqm, gather_hs<D1, FC>(sf, g1, b1), p.v1);       // operatorHE kick with the snapshot fields
+        p.v2 = fma(P.op.dtqm, gather_hs<D0, FC>(sf + (size_t)nh * FC, g0, b0), p.v2);
         deposit_h<D0, LP>(acc, nh + g0, b0, ws);                          // add_charge! (OpCharge)
         double wm = p.w * P.op.mass;                                      // OpDiag, operation for operation
         wm *= P.op.cw;
         acc.sum(0, (p.v1 * p.v1 + p.v2 * p.v2) * wm);
         acc.sum(1, p.v1 * wm);
         acc.sum(2, p.v2 * wm);
-        const double e1 = gather_h<D1>(sf + 2 * nh, g1, b1);
-        const double e2 = gather_h<D0>(sf + 3 * nh, g0, b0);
-        const double bf = gather_h<D1>(sf + 4 * nh, g1, b1);
+        const double e1 = gather_hs<D1, FC>(sf + (size_t)2 * nh * FC, g1, b1);
+        const double e2 = gather_hs<D0, FC>(sf + (size_t)3 * nh * FC, g0, b0);
+        const double bf = gather_hs<D1, FC>(sf + (size_t)4 * nh * FC, g1, b1);
         const double wq = P.op.charge * p.w * P.op.cw;
         acc.sum(3, (p.v1 * e1 + p.v2 * e2) * wq);
         acc.sum(4, wq * p.v1 * p.v2 * bf);

@@ -766,6 +766,10 @@ int gempic_finalize(void)
     if (c.pinned) cudaFreeHost(c.pinned);
     c.pinned = nullptr;
     c.pinned_bytes = 0;
+    if (c.stage) cudaFree(c.stage);
+    c.stage = nullptr;
+    c.stage_n = 0;
+    c.stage_busy = false;
     cudaStreamDestroy(c.stream);
     c.stream = nullptr;
     c.ready = false;
