@@ -13,12 +13,12 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
 
-def main(n_dev, out):
+def main(n_dev, out, force_md=False):
     gp = ge.load_package()
-    if n_dev == 1:
+    if n_dev == 1 and not force_md:
         gp.init(0)
     else:
-        gp.init_devices(n_dev)
+        gp.init_devices(n_dev)      # also with ONE device: every call then goes through the dispatcher and a worker thread
     assert gp.device_count() == n_dev
     res = {}
     nx, L = 32, 4 * math.pi
@@ -101,4 +101,4 @@ def main(n_dev, out):
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]), sys.argv[2])
+    main(int(sys.argv[1]), sys.argv[2], force_md="--md" in sys.argv[3:])

@@ -29,7 +29,7 @@ def test_sharded_equals_unsharded(tmp_path, nproc):
     assert res["ok"], res
 
 
-@pytest.mark.parametrize("n_dev", [2, 4, 8])
+@pytest.mark.parametrize("n_dev", [1, 2, 4, 8])
 def test_one_process_drives_all_devices(tmp_path, n_dev):
     """gempic_init_devices: ONE host process, n devices, unchanged API (global particle counts, global arrays).  The same
     script (tests/md_worker.py: device samplers, fused 1d2v steps with the diagnostics loop, Boris, 2d3v with the riding
@@ -44,12 +44,14 @@ def test_one_process_drives_all_devices(tmp_path, n_dev):
         pytest.skip(f"needs {n_dev} GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = {}
-    for n in (1, n_dev):
-        outs[n] = str(tmp_path / f"md{n}.npz")
-        r = subprocess.run([sys.executable, os.path.join(root, "tests", "md_worker.py"), str(n), outs[n]], cwd=root,
+    # reference: plain gempic_init on one device; under test: gempic_init_devices(n_dev) -- with n_dev = 1 the same
+    # single device, but every call goes through the dispatcher and a worker thread (runs on a one-GPU box too)
+    for key, n, extra in (("ref", 1, []), ("md", n_dev, ["--md"])):
+        outs[key] = str(tmp_path / f"md_{key}.npz")
+        r = subprocess.run([sys.executable, os.path.join(root, "tests", "md_worker.py"), str(n), outs[key]] + extra, cwd=root,
                            capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    a, b = np.load(outs[1]), np.load(outs[n_dev])
+    a, b = np.load(outs["ref"]), np.load(outs["md"])
     assert set(a.files) == set(b.files)
     for k in a.files:
         x, y = a[k], b[k]
