@@ -31,6 +31,7 @@
 
 #include "hostutil.hpp"
 #include "objects.cuh"
+#include "tma.cuh"
 
 namespace gempic {
 
@@ -1052,36 +1053,12 @@ __device__ __forceinline__ void fast_flush(FastAcc<D0, HP3, HP2> &A, int bcx, in
 // of the next kTmaStages iterations are in flight whatever the register budget; lane 0 issues, all lanes wait.
 constexpr int kTmaStages = 4, kTmaRows = 6, kTmaTile = 64;
 constexpr size_t kTmaWarpBytes = (size_t)kTmaStages * kTmaRows * kTmaTile * sizeof(double) + kTmaStages * sizeof(unsigned long long);
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity)
-{
-    unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 // lane 0: arm stage `st` and start the six row copies of the 64-particle tile that begins at particle i0
 __device__ __forceinline__ void tma_issue(const Rows2 &r, double *buf, unsigned long long *bars, int st, int64_t i0, int64_t hi)
 {
     const int cnt = (int)min((int64_t)kTmaTile, hi - i0);
     const unsigned bytes = (unsigned)(((cnt + 1) & ~1) * sizeof(double));   // 16-byte granules (rows are padded to 32 doubles)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // the tile's previous contents have been read
+    fence_proxy_async();                                                    // the tile's previous contents have been read
     mbar_expect_tx(bars + st, kTmaRows * bytes);
     double *dst = buf + (size_t)st * kTmaRows * kTmaTile;
     const double *src[kTmaRows] = {r.x[0], r.x[1], r.v[0], r.v[1], r.v[2], r.w};
@@ -1115,7 +1092,7 @@ __global__ void __launch_bounds__(kThreads2, MINB) k2_sorted(const __grid_consta
         if (lane == 0) {
 #pragma unroll
             for (int st = 0; st < kTmaStages; ++st) mbar_init(tbar + st, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_fence_init();
         }
         __syncwarp();
     }
@@ -1143,9 +1120,7 @@ __global__ void __launch_bounds__(kThreads2, MINB) k2_sorted(const __grid_consta
                 // wait for the tile of this iteration, take the two particles of the lane, hand the stage back to the copies
                 const int st = tcount % kTmaStages;
                 const unsigned parity = (tcount / kTmaStages) & 1u;
-                unsigned spins = 0;
-                while (!mbar_try_wait(tbar + st, parity))
-                    if (++spins > (1u << 26)) __trap();   // a lost copy must not hang the GPU
+                mbar_wait(tbar + st, parity);
                 const double *t = tbuf + (size_t)st * kTmaRows * kTmaTile;
                 if (ha) { a.x[0] = t[lane]; a.x[1] = t[kTmaTile + lane]; a.v[0] = t[2 * kTmaTile + lane]; a.v[1] = t[3 * kTmaTile + lane]; a.v[2] = t[4 * kTmaTile + lane]; a.w = t[5 * kTmaTile + lane]; }
                 if (hb) { b.x[0] = t[32 + lane]; b.x[1] = t[kTmaTile + 32 + lane]; b.v[0] = t[2 * kTmaTile + 32 + lane]; b.v[1] = t[3 * kTmaTile + 32 + lane]; b.v[2] = t[4 * kTmaTile + 32 + lane]; b.w = t[5 * kTmaTile + 32 + lane]; }

@@ -1,5 +1,7 @@
 // launch.cuh -- host-side launch planning for k_pass instantiations.
 #pragma once
+#include <cstdlib>
+
 #include "ops1d.cuh"
 
 namespace gempic {
@@ -58,10 +60,18 @@ inline LaunchInfo plan_pass(const PassParams<Op> &P)
     return L;
 }
 
-template <class Op, bool LP>
+// GEMPIC_K1_TMA=1: the 256-thread deposit passes (fused Strang pass, Boris step) stream their rows with cp.async.bulk
+// instead of the register prefetch (round-2 experiment; slower, see DESIGN.md section 6, so off by default)
+inline bool pass_tma_wanted()
+{
+    static const bool on = [] { const char *e = getenv("GEMPIC_K1_TMA"); return e && e[0] == '1'; }();
+    return on;
+}
+
+template <class Op, bool LP, bool TMA = false>
 inline int configure_kernel(size_t smem)
 {
-    auto kern = k_pass<Op, LP>;
+    auto kern = k_pass<Op, LP, TMA>;
     if (smem > 48 * 1024) ensure_func_smem((const void *)kern, smem);
     int per_sm = 0;
     GP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, op_threads<Op>::value, smem));
@@ -87,7 +97,17 @@ inline void launch_pass(PassParams<Op> P, PartialScratch *scratch, double *out, 
         return;
     }
     LaunchInfo L = plan_pass(P);
-    const int per_sm = L.lane_private ? configure_kernel<Op, true>(L.smem) : configure_kernel<Op, false>(L.smem);
+    bool tma = false;
+    if constexpr (Op::DEPOSIT && op_threads<Op>::value == 256)
+        tma = pass_tma_wanted() && L.lane_private && L.smem + pass_tma_bytes<Op>() <= kSmemMaxOptin;
+    if (tma) L.smem += pass_tma_bytes<Op>();
+    int per_sm;
+    if constexpr (Op::DEPOSIT && op_threads<Op>::value == 256) {
+        per_sm = tma ? configure_kernel<Op, true, true>(L.smem)
+                     : (L.lane_private ? configure_kernel<Op, true>(L.smem) : configure_kernel<Op, false>(L.smem));
+    } else {
+        per_sm = L.lane_private ? configure_kernel<Op, true>(L.smem) : configure_kernel<Op, false>(L.smem);
+    }
     GP_REQUIRE(per_sm >= 1, GEMPIC_EINVAL, "pass does not fit on an SM (smem %zu B)", L.smem);
     int grid = c.sm_count * per_sm;
     const int64_t pairs = (P.n_particles + 1) / 2;
@@ -97,10 +117,14 @@ inline void launch_pass(PassParams<Op> P, PartialScratch *scratch, double *out, 
     P.copies = L.copies;
     if (Op::DEPOSIT) P.partials = scratch->ensure((size_t)grid * n_out);
     if (tag) profile_begin(tag);
-    if (L.lane_private)
-        k_pass<Op, true><<<grid, kThreads, L.smem, c.stream>>>(P);
-    else
-        k_pass<Op, false><<<grid, kThreads, L.smem, c.stream>>>(P);
+    if constexpr (Op::DEPOSIT && op_threads<Op>::value == 256) {
+        if (tma) k_pass<Op, true, true><<<grid, kThreads, L.smem, c.stream>>>(P);
+        else if (L.lane_private) k_pass<Op, true><<<grid, kThreads, L.smem, c.stream>>>(P);
+        else k_pass<Op, false><<<grid, kThreads, L.smem, c.stream>>>(P);
+    } else {
+        if (L.lane_private) k_pass<Op, true><<<grid, kThreads, L.smem, c.stream>>>(P);
+        else k_pass<Op, false><<<grid, kThreads, L.smem, c.stream>>>(P);
+    }
     GP_CUDA(cudaGetLastError());
     if (tag) profile_end(tag);
     count_launch();

@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "splines.cuh"
+#include "tma.cuh"
 
 namespace gempic {
 
@@ -171,7 +172,15 @@ __device__ __forceinline__ void apply4(Particle &a0, Particle &a1, Particle &b0,
     }
 }
 
-template <class Op, bool LP>
+// shared memory of the TMA row stream of k_pass (TMA = true): per warp one tile of 2 batches x 4 rows x 64 doubles
+// (the pairs of both batches of an iteration) and one mbarrier
+constexpr int kPassTileDoubles = 2 * 4 * 64;
+template <class Op>
+__host__ __device__ constexpr size_t pass_tma_bytes() { return (size_t)(op_threads<Op>::value / 32) * (kPassTileDoubles * sizeof(double) + 8); }
+
+// TMA (deposit ops only, experiment of round 2): instead of prefetching the next iteration's rows into registers, every
+// warp streams them into its shared-memory tile with cp.async.bulk (one 512 B copy per row and batch) one iteration ahead.
+template <class Op, bool LP, bool TMA = false>
 __global__ void __launch_bounds__(op_threads<Op>::value) k_pass(const __grid_constant__ PassParams<Op> P)
 {
     constexpr int kThreads = op_threads<Op>::value, kNW = kThreads / 32, kH = op_halo<Op>::value,
@@ -214,7 +223,56 @@ __global__ void __launch_bounds__(op_threads<Op>::value) k_pass(const __grid_con
     const int64_t n_pairs = P.n_particles >> 1;
     const int64_t T = (int64_t)gridDim.x * kThreads;
     int64_t p = (int64_t)blockIdx.x * kThreads + tid;
-    if (Op::DEPOSIT) {
+    if constexpr (Op::DEPOSIT && TMA) {
+        const int warp = tid >> 5, lane = tid & 31;
+        double *tile = sacc + acc_words + (size_t)warp * kPassTileDoubles;
+        unsigned long long *bar = reinterpret_cast<unsigned long long *>(sacc + acc_words + (size_t)kNW * kPassTileDoubles) + warp;
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        const double *rows[4] = {P.r.x, P.r.v1, P.r.v2, P.r.w};
+        constexpr int bits[4] = {ROW_X, ROW_V1, ROW_V2, ROW_W};
+        constexpr int n_rows = ((Op::READ & ROW_X) != 0) + ((Op::READ & ROW_V1) != 0) + ((Op::READ & ROW_V2) != 0) + ((Op::READ & ROW_W) != 0);
+        auto issue = [&](int64_t pw) {   // lane 0: the 32 pairs from pw and the 32 pairs from pw + T, every row the op reads
+            fence_proxy_async();
+            mbar_expect_tx(bar, n_rows * 2 * 512);
+#pragma unroll
+            for (int bt = 0; bt < 2; ++bt)
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (Op::READ & bits[r]) bulk_g2s(tile + (bt * 4 + r) * 64, rows[r] + 2 * (pw + bt * T), 512, bar);
+        };
+        auto take = [&](int bt, Particle &u, Particle &v) {
+            const double2 *t = reinterpret_cast<const double2 *>(tile + bt * 4 * 64) + lane;
+            if (Op::READ & ROW_X) { const double2 q = t[0]; u.x = q.x; v.x = q.y; }
+            if (Op::READ & ROW_V1) { const double2 q = t[32]; u.v1 = q.x; v.v1 = q.y; }
+            if (Op::READ & ROW_V2) { const double2 q = t[64]; u.v2 = q.x; v.v2 = q.y; }
+            if (Op::READ & ROW_W) { const double2 q = t[96]; u.w = q.x; v.w = q.y; }
+        };
+        int64_t pw = p - lane;   // first pair of the warp's batch
+        unsigned phase = 0;
+        bool have = pw + 31 + T < n_pairs;
+        if (have && lane == 0) issue(pw);
+        while (have) {
+            Particle a0, a1, b0, b1;
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            take(0, a0, a1);
+            take(1, b0, b1);
+            __syncwarp();
+            const int64_t q = pw + 2 * T;
+            const bool have_next = q + 31 + T < n_pairs;
+            if (have_next && lane == 0) issue(q);
+            apply4<Op, LP>(a0, a1, b0, b1, P, sfield, acc);
+            store_pair<Op>(P.r, pw + lane, a0, a1);
+            store_pair<Op>(P.r, pw + lane + T, b0, b1);
+            pw = q;
+            have = have_next;
+        }
+        p = pw + lane;
+    } else if (Op::DEPOSIT) {
         Particle a0, a1, b0, b1;
         bool have = p + T < n_pairs;
         if (have) {
