@@ -35,6 +35,9 @@
 
 namespace gempic {
 
+#ifndef K2_PASS_MINB
+#define K2_PASS_MINB 3   // resident blocks per SM of the tile passes: their 70 KB of tiles per block allow no more
+#endif
 constexpr int kR2 = 2;          // window radius (cells) around the chunk's base cell
 constexpr int kWarps2 = 4;      // warps per block
 constexpr int kThreads2 = kWarps2 * 32;
@@ -699,7 +702,7 @@ constexpr size_t warp_smem_doubles()
 }
 
 template <class Op>
-__global__ void __launch_bounds__(kThreads2, 3) k2_pass(const __grid_constant__ P2<Op> P)
+__global__ void __launch_bounds__(kThreads2, K2_PASS_MINB) k2_pass(const __grid_constant__ P2<Op> P)
 {
     extern __shared__ double smem[];
     constexpr int SLOTS = Tile<Op::D>::SLOTS, W = Tile<Op::D>::W, WS = Tile<Op::D>::WS, FS = Tile<Op::D>::FS;
