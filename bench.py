@@ -16,7 +16,8 @@ value     device-resident path (fields stay on the GPU): a region of K steps tim
           (what a long run gets once the board sits at its power cap), `clocks` are sampled over all of them.
 e2e       the reference-facing call with HOST field buffers: every step copies e1,e2,b host->device and back inside
           the timed region (gempic_hs_strang_splitting_host), exactly what the Julia shim does for the aliased
-          e_dofs / b_dofs arrays.  `e2e_loop` is the example's whole loop body
+          e_dofs / b_dofs arrays; regions of K calls repeated for >= 1 s like `value`, median reported
+          (`first_region_value`: the burst figure before the power cap bites).  `e2e_loop` is the example's whole loop body
           (examples/strong_landau_damping_1d2v.jl:46-59): strang_splitting!; solve_poisson!; write_step! per step.
 roofline  the pass with the largest share of the step (the fused pass: 56 algorithmic B/particle) over
           its mean device time, CUDA events around every launch inside the timed regions.
@@ -478,17 +479,22 @@ def e2e_1d(B, S, steps, fuse):
         hh = gp.HamiltonianSplitting(1, 2, S["mx"], S["ks0"], S["ks1"], S["pg"], [S["e1"], S["e2"]], S["b"], resident=False, fuse=fuse)
     for _ in range(3):
         hh.strang_splitting(DT, 1)
-    dc.barrier()
-    gp.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        hh.strang_splitting(DT, 1)      # synchronous: H2D fields, pass(es) + solves, D2H fields
-    gp.synchronize()
-    sec = dc.max_over_ranks(time.perf_counter() - t0)
+    # like the device-resident measurement: regions of `steps` calls repeated until >= min_seconds, median region reported
+    secs = []
+    while sum(secs) < B.args.min_seconds and len(secs) < 64:
+        dc.barrier()
+        gp.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            hh.strang_splitting(DT, 1)      # synchronous: H2D fields, pass(es) + solves, D2H fields
+        gp.synchronize()
+        secs.append(dc.max_over_ranks(time.perf_counter() - t0))
+    sec = statistics.median(secs)
     out = {"value": S["n_global"] * steps / sec, "unit": "particle-steps/s", "h2d_bytes_per_step": 3 * NX * 8,
-           "d2h_bytes_per_step": 3 * NX * 8, "steps": steps,
+           "d2h_bytes_per_step": 3 * NX * 8, "steps": steps, "regions": len(secs),
+           "first_region_value": S["n_global"] * steps / secs[0],
            "what": ("gempic_boris_strang_splitting_host" if S["wl"]["integrator"] == "boris" else "gempic_hs_strang_splitting_host") +
-                   ": host e1,e2,b in, e1,e2,b out, synchronous"}
+                   ": host e1,e2,b in, e1,e2,b out, synchronous; median of the regions (wall clock, max over ranks)"}
     S["h_host"] = hh
     return out
 
